@@ -1,0 +1,92 @@
+// qb_common.cuh -- shared device-side definitions of the qoipp_b200 kernels (sm_100a).
+//
+// The kernels are single-pass chained scans: every tile publishes small "aggregate" words, looks back over
+// its predecessors' words and then publishes "inclusive" words (decoupled look-back).  Every word that
+// crosses CTAs is ONE 64-bit value carrying {payload, status, launch epoch}, so a relaxed 64-bit load sees a
+// consistent snapshot and no memset is needed between launches (a stale epoch reads as "not ready").
+//
+// The same sources compile under tests/emu/cuda_emu.h (QB_EMU) so the kernel logic can be stepped on a CPU.
+#pragma once
+
+#include <stdint.h>
+
+#ifndef QB_EMU
+#include <cuda_runtime.h>
+#define QB_SPIN_YIELD() __nanosleep(32)
+#define QB_DYN_SMEM qb_dyn_smem
+extern __shared__ __align__(128) unsigned char qb_dyn_smem[];
+#endif
+
+namespace qb
+{
+    constexpr unsigned kFull = 0xffffffffu;
+
+    // ---- QOI constants (reference: source/util.hpp:27-55, include/qoipp/common.hpp:17-23)
+    constexpr unsigned kOpIndex = 0x00, kOpDiff = 0x40, kOpLuma = 0x80, kOpRun = 0xC0, kOpRgb = 0xFE, kOpRgba = 0xFF;
+    constexpr unsigned kHeader = 14, kMarker = 8, kRunLimit = 62;
+    constexpr unsigned kStartPixel = 0xFF000000u;  // {0,0,0,255} as little-endian r|g<<8|b<<16|a<<24
+
+    // util::hash (source/util.hpp:347-351) reduced mod 64: one dp4a on the packed pixel
+    __device__ __forceinline__ unsigned slot_of(unsigned px) { return __dp4a(px, 0x0B070503u, 0u) & 63u; }
+
+    // a value that can never be stored in table slot `s` (its own slot differs): marks "no writer yet"
+    __device__ __forceinline__ unsigned sentinel(unsigned s) { return s == 0 ? 1u : 0u; }
+
+    // ---- cross-CTA words.  Layout: [31:0] payload-lo | [33:32] status | [53:34] epoch | [63:54] payload-hi(10b)
+    // 42-bit payloads (byte offsets, pixel indices) use lo + hi.
+    enum : unsigned { ST_NONE = 0, ST_AGG_EMPTY = 1, ST_AGG = 2, ST_INCL = 3 };
+    constexpr unsigned kEpochBits = 20, kEpochMask = (1u << kEpochBits) - 1;
+
+    __device__ __forceinline__ uint64_t pack_word(uint64_t payload42, unsigned status, unsigned epoch)
+    {
+        return (payload42 & 0xffffffffull) | ((uint64_t)status << 32) | ((uint64_t)(epoch & kEpochMask) << 34) |
+               ((payload42 >> 32) << 54);
+    }
+    __device__ __forceinline__ unsigned word_status(uint64_t w, unsigned epoch)
+    {
+        return (((unsigned)(w >> 34)) & kEpochMask) == (epoch & kEpochMask) ? ((unsigned)(w >> 32) & 3u) : ST_NONE;
+    }
+    __device__ __forceinline__ uint64_t word_payload(uint64_t w) { return (w & 0xffffffffull) | ((w >> 54) << 32); }
+
+    __device__ __forceinline__ uint64_t ld_word(const uint64_t* p)
+    {
+#ifdef QB_EMU
+        return *p;
+#else
+        uint64_t v;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        return v;
+#endif
+    }
+    __device__ __forceinline__ void st_word(uint64_t* p, uint64_t v)
+    {
+#ifdef QB_EMU
+        *p = v;
+#else
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+    }
+    // spin until the word is valid for this epoch
+    __device__ __forceinline__ uint64_t wait_word(const uint64_t* p, unsigned epoch)
+    {
+        uint64_t w = ld_word(p);
+        while (word_status(w, epoch) == ST_NONE) {
+            QB_SPIN_YIELD();
+            w = ld_word(p);
+        }
+        return w;
+    }
+
+    __device__ __forceinline__ unsigned lanemask_lt(unsigned lane) { return (1u << lane) - 1u; }
+    __device__ __forceinline__ unsigned lanemask_gt(unsigned lane) { return lane == 31 ? 0u : ~((2u << lane) - 1u); }
+
+    // bytewise (mod 256) subtract / add on packed pixels
+    __device__ __forceinline__ unsigned sub4(unsigned a, unsigned b)
+    {
+        return ((a | 0x80808080u) - (b & 0x7f7f7f7fu)) ^ ((a ^ ~b) & 0x80808080u);
+    }
+    __device__ __forceinline__ unsigned add4(unsigned a, unsigned b)
+    {
+        return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
+    }
+}  // namespace qb
