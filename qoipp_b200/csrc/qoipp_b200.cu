@@ -1,0 +1,364 @@
+// qoipp_b200.cu -- the C ABI of include/qoipp_b200.h: context/workspace management and kernel launches.
+// Compiled for sm_100a only (see __graft_entry__.build()).  No CPU fallback: every codec entry point needs a
+// CUDA device and fails with a negative cudaError_t (or BadAlloc) otherwise.
+#include "../../include/qoipp_b200.h"
+
+#include "decode_kernel.cuh"
+#include "encode_kernel.cuh"
+#include "host_util.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace qb;
+namespace H = qb::host;
+
+namespace
+{
+    constexpr int kEncK = 8;  // pixels per thread per tile: tile = 2048 pixels
+
+    int32_t cuda_code(cudaError_t e)
+    {
+        if (e == cudaSuccess) return 0;
+        if (e == cudaErrorMemoryAllocation) return H::BadAlloc;
+        return -(int32_t)e;
+    }
+#define QB_CUDA(expr)                                  \
+    do {                                               \
+        cudaError_t qb_e_ = (expr);                    \
+        if (qb_e_ != cudaSuccess) {                    \
+            (void)cudaGetLastError();                  \
+            return cuda_code(qb_e_);                   \
+        }                                              \
+    } while (0)
+
+    struct DevBuf {
+        void*  p   = nullptr;
+        size_t cap = 0;
+        // grow-only; contents are NOT preserved.  `zero` clears the new allocation.
+        cudaError_t reserve(size_t n, bool zero = false)
+        {
+            if (n <= cap) return cudaSuccess;
+            if (p) cudaFree(p);
+            p = nullptr, cap = 0;
+            size_t      want = std::max<size_t>(n + n / 4, 4096);
+            cudaError_t e    = cudaMalloc(&p, want);
+            if (e != cudaSuccess) { p = nullptr; return e; }
+            cap = want;
+            if (zero) return cudaMemset(p, 0, want);
+            return cudaSuccess;
+        }
+        void release()
+        {
+            if (p) cudaFree(p);
+            p = nullptr, cap = 0;
+        }
+    };
+
+    struct PinnedBuf {
+        void*  p   = nullptr;
+        size_t cap = 0;
+        cudaError_t reserve(size_t n)
+        {
+            if (n <= cap) return cudaSuccess;
+            if (p) cudaFreeHost(p);
+            p = nullptr, cap = 0;
+            size_t      want = std::max<size_t>(n + n / 4, 4096);
+            cudaError_t e    = cudaMallocHost(&p, want);
+            if (e != cudaSuccess) { p = nullptr; return e; }
+            cap = want;
+            return cudaSuccess;
+        }
+        void release()
+        {
+            if (p) cudaFreeHost(p);
+            p = nullptr, cap = 0;
+        }
+    };
+}  // namespace
+
+struct qoipp_b200_ctx {
+    int      device = 0;
+    int      sm_count = 148;
+    uint32_t epoch  = 0;  // launch counter for the cross-CTA words (20 bits, see qb_common.cuh)
+    DevBuf   carry;       // tile carry words of the kernel in flight (encode or decode)
+    DevBuf   tickets;     // [0] encode ticket, [1..] decode tickets
+    DevBuf   results;     // EncResult[n_images] / DecResult
+    DevBuf   state;       // EncState / DecState carry-in for the resumable calls
+    DevBuf   aux;         // decode: per-tile entry table etc.
+    DevBuf   stage_in, stage_out;  // device staging of the host-pointer calls
+    PinnedBuf h_result;   // pinned landing zone for result structs
+    PinnedBuf h_pin_in, h_pin_out;
+    cudaStream_t own_stream = nullptr;
+    bool     enc_trivial = false;  // last encode needed no launch (capacity below the header)
+    bool     attrs_set   = false;
+
+    // next epoch; the carry buffer is cleared when the 20-bit counter wraps or the buffer was (re)allocated
+    cudaError_t next_epoch(size_t carry_bytes, cudaStream_t s)
+    {
+        const bool grew = carry_bytes > carry.cap;
+        if (grew) {
+            cudaError_t e = cudaStreamSynchronize(s);  // an earlier launch may still read the old buffer
+            if (e != cudaSuccess) return e;
+            e = carry.reserve(carry_bytes, true);
+            if (e != cudaSuccess) return e;
+        }
+        epoch = (epoch + 1) & kEpochMask;
+        if (epoch == 0) {
+            cudaError_t e = cudaMemsetAsync(carry.p, 0, carry.cap, s);
+            if (e != cudaSuccess) return e;
+            epoch = 1;
+        }
+        return cudaSuccess;
+    }
+};
+
+namespace
+{
+    template <typename Kern>
+    cudaError_t allow_smem(Kern k, size_t bytes)
+    {
+        return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    }
+
+    cudaError_t set_attrs(qoipp_b200_ctx* c)
+    {
+        if (c->attrs_set) return cudaSuccess;
+        cudaError_t e;
+        if ((e = allow_smem(encode_kernel<3, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
+        if ((e = allow_smem(encode_kernel<4, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
+        if ((e = dec_set_attrs()) != cudaSuccess) return e;
+        c->attrs_set = true;
+        return cudaSuccess;
+    }
+
+    struct Guard {  // selects the context's device for the duration of a call
+        int prev = -1;
+        explicit Guard(int dev)
+        {
+            cudaGetDevice(&prev);
+            if (prev != dev) cudaSetDevice(dev);
+            else prev = -1;
+        }
+        ~Guard()
+        {
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+    };
+
+    // ---- encode launch shared by the one-shot, batch and resumable entry points
+    int32_t launch_encode(qoipp_b200_ctx* c, const uint8_t* d_in, uint64_t in_stride, uint32_t n_images, uint64_t n_pixels,
+                          unsigned ch, const uint8_t* header14, uint8_t* d_out, uint64_t out_stride, uint64_t out_cap,
+                          uint32_t flags, const EncState* d_init, cudaStream_t s)
+    {
+        QB_CUDA(set_attrs(c));
+        constexpr uint64_t T = (uint64_t)kEncThreads * kEncK;
+        const uint64_t     tiles = (n_pixels + T - 1) / T;
+        if (tiles * n_images >= (1ull << 31)) return H::TooBig;
+        QB_CUDA(c->results.reserve(sizeof(EncResult) * n_images));
+        QB_CUDA(c->tickets.reserve(64, true));
+        QB_CUDA(c->next_epoch(tiles * n_images * kEncDescWords * sizeof(uint64_t), s));
+        EncParams P{};
+        P.in = d_in, P.out = d_out;
+        P.n_pixels = n_pixels, P.in_stride = in_stride, P.out_stride = out_stride, P.out_cap = out_cap;
+        P.tiles_per_image = (uint32_t)tiles, P.n_images = n_images, P.epoch = c->epoch, P.flags = flags;
+        if (header14) std::memcpy(P.header, header14, 14);
+        P.init_state = d_init;
+        P.results    = static_cast<EncResult*>(c->results.p);
+        P.desc       = static_cast<uint64_t*>(c->carry.p);
+        P.ticket     = static_cast<uint32_t*>(c->tickets.p);
+        const dim3 grid((unsigned)(tiles * n_images)), block(kEncThreads);
+        if (ch == 3) encode_kernel<3, kEncK><<<grid, block, sizeof(EncSmem<kEncK>), s>>>(P);
+        else encode_kernel<4, kEncK><<<grid, block, sizeof(EncSmem<kEncK>), s>>>(P);
+        QB_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    unsigned pack_px(const uint8_t* p) { return p[0] | (unsigned)p[1] << 8 | (unsigned)p[2] << 16 | (unsigned)p[3] << 24; }
+    void     unpack_px(unsigned v, uint8_t* p) { p[0] = (uint8_t)v, p[1] = (uint8_t)(v >> 8), p[2] = (uint8_t)(v >> 16), p[3] = (uint8_t)(v >> 24); }
+}  // namespace
+
+extern "C"
+{
+    int32_t     qoipp_b200_version(void) { return QOIPP_B200_VERSION; }
+    const char* qoipp_b200_error_string(int32_t code) { return H::error_string(code); }
+
+    int32_t qoipp_b200_device_count(void)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return 0;
+        }
+        return n;
+    }
+
+    int32_t qoipp_b200_count_bytes(const qoipp_b200_desc* desc, uint64_t* out) { return H::count_bytes(*desc, out); }
+    int32_t qoipp_b200_worst_size(const qoipp_b200_desc* desc, uint64_t* out) { return H::worst_size(*desc, out); }
+    int32_t qoipp_b200_read_header(const uint8_t* h_qoi, uint64_t size, qoipp_b200_desc* out) { return H::read_header(h_qoi, size, out); }
+
+    int32_t qoipp_b200_ctx_create(int32_t device, qoipp_b200_ctx** out)
+    {
+        *out = nullptr;
+        int n = 0;
+        QB_CUDA(cudaGetDeviceCount(&n));
+        if (device < 0 || device >= n) return -(int32_t)cudaErrorInvalidDevice;
+        auto* c = new (std::nothrow) qoipp_b200_ctx();
+        if (!c) return H::BadAlloc;
+        c->device = device;
+        Guard g(device);
+        cudaDeviceProp prop{};
+        cudaError_t    e = cudaGetDeviceProperties(&prop, device);
+        if (e == cudaSuccess && prop.major < 10) {
+            std::fprintf(stderr, "qoipp_b200: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor);
+            e = cudaErrorNoKernelImageForDevice;
+        }
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = c->h_result.reserve(4096);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            delete c;
+            return cuda_code(e);
+        }
+        c->sm_count = prop.multiProcessorCount;
+        *out        = c;
+        return 0;
+    }
+
+    int32_t qoipp_b200_ctx_destroy(qoipp_b200_ctx* c)
+    {
+        if (!c) return 0;
+        Guard g(c->device);
+        cudaDeviceSynchronize();
+        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release();
+        c->stage_in.release(), c->stage_out.release();
+        c->h_result.release(), c->h_pin_in.release(), c->h_pin_out.release();
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
+        delete c;
+        return 0;
+    }
+
+    // ------------------------------------------------------------------ encode
+    int32_t qoipp_b200_encode_dev(qoipp_b200_ctx* c, const uint8_t* d_raw, const qoipp_b200_desc* desc, uint8_t* d_out,
+                                  uint64_t out_cap, void* stream)
+    {
+        uint64_t raw;
+        if (int32_t e = H::count_bytes(*desc, &raw)) return e;
+        Guard g(c->device);
+        c->enc_trivial = out_cap < H::kHeaderSize;  // util.hpp:125-131: the header chunk does not fit, nothing is stored
+        if (c->enc_trivial) return 0;
+        uint8_t hdr[14];
+        H::write_header(*desc, hdr);
+        return launch_encode(c, d_raw, 0, 1, (uint64_t)desc->width * desc->height, desc->channels, hdr, d_out, 0, out_cap, 0,
+                             nullptr, static_cast<cudaStream_t>(stream));
+    }
+
+    int32_t qoipp_b200_encode_status(qoipp_b200_ctx* c, void* stream, uint64_t* written, int32_t* complete)
+    {
+        if (c->enc_trivial) {
+            *written = 0, *complete = 0;
+            return 0;
+        }
+        Guard g(c->device);
+        auto  s = static_cast<cudaStream_t>(stream);
+        auto* h = static_cast<EncResult*>(c->h_result.p);
+        QB_CUDA(cudaMemcpyAsync(h, c->results.p, 24, cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        *written  = h->written;
+        *complete = (int32_t)h->complete;
+        return 0;
+    }
+
+    int32_t qoipp_b200_encode_host(qoipp_b200_ctx* c, const uint8_t* h_raw, uint64_t raw_size, const qoipp_b200_desc* desc,
+                                   uint8_t* h_out, uint64_t out_cap, uint64_t* written, int32_t* complete)
+    {
+        // validation order of qoipp::encode_into, source/simple.cpp:235-244
+        if (raw_size == 0) return H::Empty;
+        uint64_t need, worst;
+        if (int32_t e = H::count_bytes(*desc, &need)) return e;
+        if (raw_size != need) return H::MismatchedDesc;
+        H::worst_size(*desc, &worst);
+        Guard          g(c->device);
+        const uint64_t cap = std::min(out_cap, worst);
+        QB_CUDA(c->stage_in.reserve(raw_size + 16));
+        QB_CUDA(c->stage_out.reserve(cap + 16));
+        cudaStream_t s = c->own_stream;
+        QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_raw, raw_size, cudaMemcpyHostToDevice, s));
+        if (int32_t e = qoipp_b200_encode_dev(c, static_cast<uint8_t*>(c->stage_in.p), desc, static_cast<uint8_t*>(c->stage_out.p), cap, s)) return e;
+        if (int32_t e = qoipp_b200_encode_status(c, s, written, complete)) return e;
+        if (*written) QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, *written, cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        return 0;
+    }
+
+    int32_t qoipp_b200_encode_batch_dev(qoipp_b200_ctx* c, const uint8_t* d_raw, uint64_t raw_stride, uint32_t n_images,
+                                        const qoipp_b200_desc* desc, uint8_t* d_out, uint64_t out_stride, uint64_t out_cap,
+                                        uint64_t* d_written, void* stream)
+    {
+        uint64_t raw;
+        if (int32_t e = H::count_bytes(*desc, &raw)) return e;
+        if (n_images == 0) return H::Empty;
+        if (out_cap < H::kHeaderSize) return H::NotEnoughSpace;
+        Guard g(c->device);
+        auto  s = static_cast<cudaStream_t>(stream);
+        uint8_t hdr[14];
+        H::write_header(*desc, hdr);
+        c->enc_trivial = false;
+        if (int32_t e = launch_encode(c, d_raw, raw_stride, n_images, (uint64_t)desc->width * desc->height, desc->channels, hdr,
+                                      d_out, out_stride, out_cap, 0, nullptr, s))
+            return e;
+        if (d_written)  // EncResult[k].written -> d_written[k]
+            QB_CUDA(cudaMemcpy2DAsync(d_written, sizeof(uint64_t), c->results.p, sizeof(EncResult), sizeof(uint64_t), n_images,
+                                      cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+
+    int32_t qoipp_b200_stream_encode_host(qoipp_b200_ctx* c, qoipp_b200_state* st, const uint8_t* h_in, uint64_t in_size,
+                                          uint8_t* h_out, uint64_t out_cap, uint64_t* processed, uint64_t* written)
+    {
+        // error order of StreamEncoder::encode, source/stream.cpp:140-146
+        if (!st->channels) return H::NotInitialized;
+        if (out_cap == 0 || in_size == 0) return H::Empty;
+        if (out_cap < 5) return H::TooShort;
+        const unsigned ch = st->channels;
+        const uint64_t n  = in_size / ch;
+        *processed = 0, *written = 0;
+        if (n == 0) return 0;
+        Guard g(c->device);
+        // a call can never store more than the worst case of its input (+1 for a pending run flush)
+        const uint64_t cap = std::min<uint64_t>(out_cap, n * (ch + 1) + 1);
+        QB_CUDA(c->stage_in.reserve(n * ch + 16));
+        QB_CUDA(c->stage_out.reserve(cap + 16));
+        QB_CUDA(c->state.reserve(sizeof(EncState)));
+        cudaStream_t s  = c->own_stream;
+        auto*        hs = reinterpret_cast<EncState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
+        hs->prev = pack_px(st->prev), hs->run = st->run;
+        for (int i = 0; i < 64; ++i) hs->table[i] = pack_px(st->seen[i]);
+        QB_CUDA(cudaMemcpyAsync(c->state.p, hs, sizeof(EncState), cudaMemcpyHostToDevice, s));
+        QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_in, n * ch, cudaMemcpyHostToDevice, s));
+        c->enc_trivial = false;
+        if (int32_t e = launch_encode(c, static_cast<uint8_t*>(c->stage_in.p), 0, 1, n, ch, nullptr, static_cast<uint8_t*>(c->stage_out.p),
+                                      0, cap, ENC_STREAM, static_cast<EncState*>(c->state.p), s))
+            return e;
+        auto* hr = static_cast<EncResult*>(c->h_result.p);
+        QB_CUDA(cudaMemcpyAsync(hr, c->results.p, sizeof(EncResult), cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        if (hr->written) {
+            QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, hr->written, cudaMemcpyDeviceToHost, s));
+            QB_CUDA(cudaStreamSynchronize(s));
+        }
+        *processed = hr->processed * ch;
+        *written   = hr->written;
+        unpack_px(hr->state.prev, st->prev);
+        st->run = (uint8_t)hr->state.run;
+        for (int i = 0; i < 64; ++i) unpack_px(hr->state.table[i], st->seen[i]);
+        return 0;
+    }
+}
+
+#include "decode_host.inl"

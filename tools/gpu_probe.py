@@ -1,0 +1,33 @@
+"""Scratch timing probe used during development (not the bench contract): device-timed encode of a few images."""
+import sys, time
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+from qoipp_b200 import api, synth
+from oracle.pyoracle import Oracle
+
+ctx = api.Context(0)
+st = torch.cuda.current_stream().cuda_stream
+for kind, w, h, ch in [("photo", 3840, 2160, 3), ("photo", 7680, 4320, 4), ("noise", 3840, 2160, 4), ("flat", 7680, 4320, 4), ("gradient", 7680, 4320, 3)]:
+    t0 = time.time()
+    raw = synth.generate(kind, w, h, ch)
+    d_raw = torch.from_numpy(raw).cuda()
+    cap = (ch + 1) * w * h + 22
+    d_out = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        ctx.encode_dev(d_raw, w, h, ch, 0, d_out, cap, st)
+    n, ok = ctx.encode_status(st)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    reps = 20
+    ev[0].record()
+    for _ in range(reps):
+        ctx.encode_dev(d_raw, w, h, ch, 0, d_out, cap, st)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    alg = raw.size + n
+    print(f"{kind} {w}x{h}x{ch}: {ms*1e3:.1f} us  raw {raw.size/ms/1e6:.1f} GB/s  alg {alg/ms/1e6:.1f} GB/s  ({alg/ms/1e6/6548.8*100:.1f}% of measured HBM)  E/raw={n/raw.size:.3f}  gen {time.time()-t0:.1f}s", flush=True)
+    if w <= 3840:
+        ref = Oracle.encode(raw, w, h, ch)
+        got = d_out[:n].cpu().numpy()
+        print("   parity:", n == ref.size and np.array_equal(got, ref))
