@@ -1,9 +1,173 @@
-// decode_host.inl -- placeholder until the decode kernels land (next commit).
+// decode_host.inl -- decode entry points of the C ABI (included at the end of qoipp_b200.cu).
+namespace
+{
+    // tile bookkeeping shared by the single-image and batch launches
+    int32_t launch_decode(qoipp_b200_ctx* c, DecParams& P, cudaStream_t s)
+    {
+        QB_CUDA(set_attrs(c));
+        QB_CUDA(c->tickets.reserve(64, true));
+        QB_CUDA(c->results.reserve(sizeof(DecResult) * P.n_images));
+        QB_CUDA(cudaMemsetAsync(c->results.p, 0, sizeof(DecResult) * P.n_images, s));
+        QB_CUDA(c->next_epoch((uint64_t)P.n_tiles * kDecDescWords * sizeof(uint64_t), s));
+        P.epoch   = c->epoch;
+        P.results = static_cast<DecResult*>(c->results.p);
+        P.desc    = static_cast<uint64_t*>(c->carry.p);
+        P.ticket  = static_cast<uint32_t*>(c->tickets.p) + 1;
+        decode_kernel<<<P.n_tiles, kDecThreads, sizeof(DecSmem), s>>>(P);
+        QB_CUDA(cudaGetLastError());
+        SerialParams S{};
+        S.d = P, S.mode = 0;
+        decode_serial_kernel<<<P.n_images, 32, sizeof(SerialSmem), s>>>(S);  // exits at once unless the parallel path flagged the image
+        QB_CUDA(cudaGetLastError());
+        return 0;
+    }
+}
+
 extern "C"
 {
-    int32_t qoipp_b200_decode_dev(qoipp_b200_ctx*, const uint8_t*, uint64_t, const qoipp_b200_desc*, uint8_t, int32_t, uint8_t*, uint64_t, void*) { return -(int32_t)cudaErrorNotSupported; }
-    int32_t qoipp_b200_decode_status(qoipp_b200_ctx*, void*, int32_t*) { return -(int32_t)cudaErrorNotSupported; }
-    int32_t qoipp_b200_decode_host(qoipp_b200_ctx*, const uint8_t*, uint64_t, uint8_t, int32_t, uint8_t*, uint64_t, qoipp_b200_desc*) { return -(int32_t)cudaErrorNotSupported; }
-    int32_t qoipp_b200_decode_batch_dev(qoipp_b200_ctx*, const uint8_t*, const uint64_t*, uint32_t, const qoipp_b200_desc*, uint8_t, uint8_t*, uint64_t, void*) { return -(int32_t)cudaErrorNotSupported; }
-    int32_t qoipp_b200_stream_decode_host(qoipp_b200_ctx*, qoipp_b200_state*, const uint8_t*, uint64_t, uint8_t*, uint64_t, uint64_t*, uint64_t*) { return -(int32_t)cudaErrorNotSupported; }
+    int32_t qoipp_b200_decode_dev(qoipp_b200_ctx* c, const uint8_t* d_qoi, uint64_t qoi_size, const qoipp_b200_desc* desc,
+                                  uint8_t target, int32_t flip, uint8_t* d_out, uint64_t out_cap, void* stream)
+    {
+        if (qoi_size == 0) return H::Empty;
+        if (qoi_size <= H::kHeaderSize + H::kMarkerSize) return H::TooShort;  // simple.cpp:369
+        uint64_t raw;
+        if (int32_t e = H::count_bytes(*desc, &raw)) return e;
+        const unsigned tgt = target ? target : desc->channels;
+        if (tgt != 3 && tgt != 4) return H::InvalidDesc;
+        const uint64_t n = (uint64_t)desc->width * desc->height;
+        if (out_cap < n * tgt) return H::NotEnoughSpace;
+        const uint64_t tiles = (qoi_size - H::kHeaderSize + kDecTB - 1) / kDecTB;
+        if (tiles >= (1ull << 31)) return H::TooBig;
+        Guard     g(c->device);
+        DecParams P{};
+        P.qoi = d_qoi, P.offsets = nullptr, P.tile_first = nullptr;
+        P.single[0] = 0, P.single[1] = qoi_size;
+        P.out = d_out, P.out_stride = 0, P.n_pixels = n;
+        P.width = desc->width, P.height = desc->height, P.target = tgt, P.flip = flip != 0;
+        P.n_images = 1, P.n_tiles = (uint32_t)tiles;
+        return launch_decode(c, P, static_cast<cudaStream_t>(stream));
+    }
+
+    int32_t qoipp_b200_decode_status(qoipp_b200_ctx* c, void* stream, int32_t* path)
+    {
+        Guard g(c->device);
+        auto  s = static_cast<cudaStream_t>(stream);
+        auto* h = static_cast<DecResult*>(c->h_result.p);
+        QB_CUDA(cudaMemcpyAsync(h, c->results.p, 16, cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        if (path) *path = (int32_t)h->path;
+        return 0;
+    }
+
+    int32_t qoipp_b200_decode_host(qoipp_b200_ctx* c, const uint8_t* h_qoi, uint64_t qoi_size, uint8_t target, int32_t flip,
+                                   uint8_t* h_out, uint64_t out_cap, qoipp_b200_desc* desc)
+    {
+        // check order of qoipp::decode_into, source/simple.cpp:451-474
+        if (qoi_size == 0) return H::Empty;
+        if (qoi_size <= H::kHeaderSize + H::kMarkerSize) return H::TooShort;
+        if (int32_t e = H::read_header(h_qoi, qoi_size, desc)) return e;
+        uint64_t src_bytes;
+        if (int32_t e = H::count_bytes(*desc, &src_bytes)) return e;
+        if (out_cap < src_bytes) return H::NotEnoughSpace;  // :467-471 sized with the SOURCE channel count
+        const unsigned tgt  = target ? target : desc->channels;
+        const uint64_t need = (uint64_t)desc->width * desc->height * tgt;
+        if (out_cap < need) return H::NotEnoughSpace;  // SURVEY hazard 3: the reference would write past the buffer
+        Guard g(c->device);
+        QB_CUDA(c->stage_in.reserve(qoi_size + 64));
+        QB_CUDA(c->stage_out.reserve(need + 64));
+        cudaStream_t s = c->own_stream;
+        QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_qoi, qoi_size, cudaMemcpyHostToDevice, s));
+        if (int32_t e = qoipp_b200_decode_dev(c, static_cast<uint8_t*>(c->stage_in.p), qoi_size, desc, (uint8_t)tgt, flip,
+                                              static_cast<uint8_t*>(c->stage_out.p), need, s))
+            return e;
+        QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, need, cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        desc->channels = (uint8_t)tgt;  // :476 the returned Desc carries the target
+        return 0;
+    }
+
+    int32_t qoipp_b200_decode_batch_dev(qoipp_b200_ctx* c, const uint8_t* d_qoi, const uint64_t* h_offsets, uint32_t n_images,
+                                        const qoipp_b200_desc* desc, uint8_t target, uint8_t* d_out, uint64_t out_stride,
+                                        void* stream)
+    {
+        if (n_images == 0) return H::Empty;
+        uint64_t raw;
+        if (int32_t e = H::count_bytes(*desc, &raw)) return e;
+        const unsigned tgt = target ? target : desc->channels;
+        if (tgt != 3 && tgt != 4) return H::InvalidDesc;
+        const uint64_t n = (uint64_t)desc->width * desc->height;
+        if (out_stride < n * tgt) return H::NotEnoughSpace;
+        Guard g(c->device);
+        auto  s = static_cast<cudaStream_t>(stream);
+        // per-image tile ranges: offsets (u64) then first-tile ids (u32), staged through pinned memory
+        const size_t off_bytes = sizeof(uint64_t) * (n_images + 1), tf_bytes = sizeof(uint32_t) * (n_images + 1);
+        QB_CUDA(c->h_pin_in.reserve(off_bytes + tf_bytes));
+        QB_CUDA(c->aux.reserve(off_bytes + tf_bytes));
+        QB_CUDA(cudaStreamSynchronize(s));  // the pinned table of an earlier call may still be in flight
+        auto*    ho = static_cast<uint64_t*>(c->h_pin_in.p);
+        auto*    ht = reinterpret_cast<uint32_t*>(ho + n_images + 1);
+        uint64_t tiles = 0;
+        for (uint32_t k = 0; k < n_images; ++k) {
+            const uint64_t sz = h_offsets[k + 1] - h_offsets[k];
+            if (sz <= H::kHeaderSize + H::kMarkerSize) return H::TooShort;
+            ho[k] = h_offsets[k], ht[k] = (uint32_t)tiles;
+            tiles += (sz - H::kHeaderSize + kDecTB - 1) / kDecTB;
+            if (tiles >= (1ull << 31)) return H::TooBig;
+        }
+        ho[n_images] = h_offsets[n_images], ht[n_images] = (uint32_t)tiles;
+        QB_CUDA(cudaMemcpyAsync(c->aux.p, ho, off_bytes + tf_bytes, cudaMemcpyHostToDevice, s));
+        DecParams P{};
+        P.qoi = d_qoi;
+        P.offsets    = static_cast<uint64_t*>(c->aux.p);
+        P.tile_first = reinterpret_cast<uint32_t*>(static_cast<uint64_t*>(c->aux.p) + n_images + 1);
+        P.out = d_out, P.out_stride = out_stride, P.n_pixels = n;
+        P.width = desc->width, P.height = desc->height, P.target = tgt, P.flip = 0;
+        P.n_images = n_images, P.n_tiles = (uint32_t)tiles;
+        return launch_decode(c, P, s);
+    }
+
+    int32_t qoipp_b200_stream_decode_host(qoipp_b200_ctx* c, qoipp_b200_state* st, const uint8_t* h_in, uint64_t in_size,
+                                          uint8_t* h_out, uint64_t out_cap, uint64_t* processed, uint64_t* written)
+    {
+        // error order of StreamDecoder::decode, source/stream.cpp:314-320
+        if (!st->channels) return H::NotInitialized;
+        if (out_cap == 0) return H::Empty;
+        if (out_cap < st->channels) return H::TooShort;
+        *processed = 0, *written = 0;
+        Guard          g(c->device);
+        const unsigned ch = st->channels;
+        // a call produces at most 62 pixels per input byte plus the pending run
+        const uint64_t cap = std::min<uint64_t>(out_cap, (in_size * 62 + st->run) * ch);
+        if (cap < ch) return 0;  // nothing to read and nothing pending
+        QB_CUDA(c->stage_in.reserve(in_size + 64));
+        QB_CUDA(c->stage_out.reserve(cap + 64));
+        QB_CUDA(c->state.reserve(sizeof(DecState)));
+        QB_CUDA(c->results.reserve(sizeof(DecResult)));
+        cudaStream_t s  = c->own_stream;
+        auto*        hs = reinterpret_cast<DecState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
+        hs->prev = pack_px(st->prev), hs->run = st->run;
+        for (int i = 0; i < 64; ++i) hs->table[i] = pack_px(st->seen[i]);
+        QB_CUDA(cudaMemcpyAsync(c->state.p, hs, sizeof(DecState), cudaMemcpyHostToDevice, s));
+        if (in_size) QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_in, in_size, cudaMemcpyHostToDevice, s));
+        SerialParams S{};
+        S.d.qoi = static_cast<uint8_t*>(c->stage_in.p), S.d.single[0] = 0, S.d.single[1] = in_size;
+        S.d.out = static_cast<uint8_t*>(c->stage_out.p), S.d.out_stride = cap;  // mode 1: capacity in bytes
+        S.d.target = ch, S.d.flip = 0, S.d.n_images = 1;
+        S.d.results = static_cast<DecResult*>(c->results.p);
+        S.mode = 1, S.init = static_cast<DecState*>(c->state.p), S.in_size = in_size;
+        decode_serial_kernel<<<1, 32, sizeof(SerialSmem), s>>>(S);
+        QB_CUDA(cudaGetLastError());
+        auto* hr = static_cast<DecResult*>(c->h_result.p);
+        QB_CUDA(cudaMemcpyAsync(hr, c->results.p, sizeof(DecResult), cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        if (hr->written) {
+            QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, hr->written, cudaMemcpyDeviceToHost, s));
+            QB_CUDA(cudaStreamSynchronize(s));
+        }
+        *processed = hr->processed, *written = hr->written;
+        unpack_px(hr->state.prev, st->prev);
+        st->run = (uint8_t)hr->state.run;
+        for (int i = 0; i < 64; ++i) unpack_px(hr->state.table[i], st->seen[i]);
+        return 0;
+    }
 }

@@ -1,9 +1,706 @@
-// decode_kernel.cuh -- placeholder until the decode kernels land (next commit).
+// decode_kernel.cuh -- tile-parallel QOI decoder for sm_100a (+ the exact sequential kernel it falls back on).
+//
+// Replaces the serial loop of the reference, impl::decode (source/simple.cpp:100-171).  A tile is kDecTB bytes of
+// the chunk stream, one CTA; three chained decoupled look-backs carry what the serial loop carries:
+//
+//   (1) parse carry  -- an op's length is a function of its tag byte only (simple.cpp:118-165), so a tile is a
+//                       map {entry offset 0..4 -> exit offset 0..4}; maps compose, tiles scan them.  No
+//                       self-synchronisation is assumed (a late parse of FE FE FE .. never re-syncs).
+//   (2) count carry  -- pixels produced so far (sum), and the value-free "slot / alpha" carry: util::hash
+//                       (util.hpp:347-351) is linear mod 64, so the table slot written by every op follows from
+//                       the literal ops (roots) by a segmented prefix sum of 3dr+5dg+7db without knowing pixels.
+//   (3) state carry  -- per tile a transfer function: each of the 64 table slots and `prev` leaves the tile
+//                       either as a constant or as (incoming entry e) + delta (mod 256 per channel).  These
+//                       compose, so the look-back follows one entry per thread until it meets a constant.
+//
+// Inside a tile: INDEX ops find their writer (last earlier colour op with the same slot) with
+// __match_any_sync + per-warp tables, chains of INDEX -> INDEX are collapsed by pointer jumping in shared
+// memory, DIFF/LUMA are segmented mod-256 prefix sums from their root.
+//
+// SPECULATION.  The slot of an OP_RGB pixel needs its inherited alpha.  The parallel path assumes "alpha =
+// alpha of the last OP_RGBA before it, else 255" (exact for every stream whose INDEX ops never change alpha,
+// e.g. all RGB images and opaque RGBA images) and that an INDEX op reads a slot that was written.  Every tile
+// VERIFIES both against the final pixel values; if any check fails the image is decoded again by
+// decode_serial_kernel, which is the reference loop verbatim in behaviour (one lane decodes, the warp stages I/O).
+// Verified => exact: by induction over op order, if every root's assumed slot equals the hash of its computed
+// value then every writer pointer, hence every value, is the true one.
 #pragma once
+
 #include "qb_common.cuh"
+
 namespace qb
 {
+    struct DecState {  // == StreamDecoder members (include/qoipp/stream.hpp:239-243), pixels packed
+        uint32_t prev;
+        uint32_t run;
+        uint32_t table[64];
+    };
+
+    struct DecResult {
+        uint32_t bad;   // parallel path: speculation refuted somewhere in this image
+        uint32_t path;  // 0 = parallel result stands, 1 = sequential kernel produced the pixels
+        uint64_t pixels;
+        uint64_t processed;  // resumable decode: input bytes consumed / output bytes written / carry-out
+        uint64_t written;
+        DecState state;
+    };
+
+    struct DecParams {
+        const uint8_t*  qoi;
+        const uint64_t* offsets;     // [n_images + 1] device; null => single[]
+        const uint32_t* tile_first;  // [n_images + 1] device; null => single image
+        uint64_t        single[2];
+        uint8_t*        out;
+        uint64_t        out_stride;
+        uint64_t        n_pixels;
+        uint32_t        width, height, target, flip;
+        uint32_t        n_images, n_tiles, epoch, pad;
+        DecResult*      results;
+        uint64_t*       desc;
+        uint32_t*       ticket;
+    };
+
+    constexpr int kDecThreads = 256, kDecWarps = 8, kDecSB = 8, kDecTB = kDecThreads * kDecSB;
+    constexpr int kDecDescWords = 72;
+    constexpr int kDwParse = 0, kDwPix = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
+    constexpr unsigned kMapIdentity = 0u | 1u << 3 | 2u << 6 | 3u << 9 | 4u << 12;
+
+    // link / transfer-function entry codes
+    constexpr unsigned kPtrConst = 0xFE00u, kPtrLeafSlot = 0xFF00u, kPtrLeafPrev = 0xFF40u, kNoRoot = 0xFFFFu, kNoOp = 0xFFFFu;
+    enum : unsigned { K_INDEX = 0, K_DIFF = 1, K_LUMA = 2, K_RUN = 3, K_RGB = 4, K_RGBA = 5 };
+
+    struct Seg {       // scan element of carry (2), see combine()
+        unsigned cnt;  // pixels | ops << 20
+        unsigned da;   // delta since the segment root (r,g,b bytes) | alpha of the last OP_RGBA << 24
+        unsigned fl;   // root byte position | c << 16 | has_root << 22 | uses_alpha_in << 23 | has_rgba << 24
+    };
+    constexpr unsigned kFlRoot = 1u << 22, kFlUses = 1u << 23, kFlRgba = 1u << 24;
+
+    __device__ __forceinline__ Seg seg_identity() { return Seg{ 0u, 0u, 0u }; }
+
+    // A happens before B
+    __device__ __forceinline__ Seg combine(const Seg& A, const Seg& B)
+    {
+        Seg C;
+        C.cnt                = A.cnt + B.cnt;
+        const unsigned hasA  = A.fl & kFlRgba;
+        const unsigned alphaA = A.da >> 24;
+        unsigned       alpha  = (B.fl & kFlRgba) ? (B.da >> 24) : alphaA;
+        unsigned       rgba   = (B.fl & kFlRgba) | hasA;
+        unsigned       root, delta, c, flags;
+        if (B.fl & kFlRoot) {
+            root = B.fl & 0xFFFFu, delta = B.da & 0xFFFFFFu, c = (B.fl >> 16) & 63u, flags = kFlRoot | (B.fl & kFlUses);
+            if ((B.fl & kFlUses) && hasA) c = (c + 11u * alphaA) & 63u, flags = kFlRoot;
+        } else {
+            root = A.fl & 0xFFFFu, delta = add4(A.da, B.da) & 0xFFFFFFu, c = ((A.fl >> 16) + (B.fl >> 16)) & 63u;
+            flags = A.fl & (kFlRoot | kFlUses);
+        }
+        C.da = delta | alpha << 24;
+        C.fl = root | c << 16 | flags | rgba;
+        return C;
+    }
+
+    __device__ __forceinline__ unsigned map_compose(unsigned f, unsigned g)  // f first, then g
+    {
+        unsigned r = 0;
+#pragma unroll
+        for (int e = 0; e < 5; ++e) r |= ((g >> (3u * ((f >> (3 * e)) & 7u))) & 7u) << (3 * e);
+        return r;
+    }
+
+    __device__ __forceinline__ unsigned op_length(unsigned tag)  // simple.cpp:118-165
+    {
+        return 1u + ((tag >> 6) == 2u) + 3u * (tag == kOpRgb) + 4u * (tag == kOpRgba);
+    }
+
+    struct DecSmem {
+        alignas(16) unsigned char bytes[kDecTB + 48];  // tile bytes at [shift, shift + kDecTB + 8), zero padded
+        uint64_t       link[kDecTB];                   // by byte position of a root's tag: ptr << 32 | add
+        unsigned       op_meta[kDecTB];                // pixoff | (npix-1) << 17 | kind << 23 | slot << 26
+        unsigned       op_val[kDecTB];                 // delta since the root, later the pixel value
+        unsigned short op_pos[kDecTB];
+        unsigned short op_root[kDecTB];                // byte position of the segment root, kNoRoot = before the tile
+        unsigned short wtab[kDecWarps * 64];           // per warp: op index of the last colour op per slot
+        unsigned       in_state[65], fn_code[65], fn_add[65];
+        Seg            wseg[kDecWarps];
+        unsigned       wmap[kDecWarps];
+        uint64_t       pix_base;
+        unsigned       ticket, entry, slot_in, alpha_in, n_ops, n_pix, bad, changed;
+    };
+
+    // op walk of one thread's sub-chunk: f(pos, tag) for every op whose tag lies in [8*tid, 8*tid + 8) and below `limit`
+    template <class F>
+    __device__ __forceinline__ void walk_ops(const unsigned char* b, unsigned tid, unsigned entry, unsigned limit, F&& f)
+    {
+        unsigned p = tid * kDecSB + entry;
+        const unsigned end = min((tid + 1u) * kDecSB, limit);
+        while (p < end) {
+            const unsigned tag = b[p];
+            f(p, tag);
+            p += op_length(tag);
+        }
+    }
+
+    // element of a single op for carry (2); also returns kind / npix / literal-or-delta
+    struct OpInfo {
+        unsigned kind, npix, data, lin;  // data: literal (RGB: alpha byte 0) or delta bytes; lin: slot contribution
+    };
+    __device__ __forceinline__ OpInfo op_info(const unsigned char* b, unsigned p, unsigned tag)
+    {
+        OpInfo o;
+        o.npix = 1, o.data = 0, o.lin = 0;
+        if (tag == kOpRgb) {
+            o.kind = K_RGB;
+            o.data = b[p + 1] | (unsigned)b[p + 2] << 8 | (unsigned)b[p + 3] << 16;
+            o.lin  = __dp4a(o.data, 0x00070503u, 0u) & 63u;
+        } else if (tag == kOpRgba) {
+            o.kind = K_RGBA;
+            o.data = b[p + 1] | (unsigned)b[p + 2] << 8 | (unsigned)b[p + 3] << 16 | (unsigned)b[p + 4] << 24;
+            o.lin  = slot_of(o.data);
+        } else {
+            const unsigned hi = tag >> 6;
+            if (hi == 0) {
+                o.kind = K_INDEX, o.lin = tag & 63u;
+            } else if (hi == 1) {  // simple.cpp:136-144
+                o.kind = K_DIFF;
+                o.data = add4(((tag >> 4) & 3u) | ((tag >> 2) & 3u) << 8 | (tag & 3u) << 16, 0x00FEFEFEu);
+                o.lin  = __dp4a(o.data, 0x00070503u, 0u) & 63u;
+            } else if (hi == 2) {  // simple.cpp:145-155
+                o.kind            = K_LUMA;
+                const unsigned rb = b[p + 1];
+                const unsigned vg = ((tag & 63u) + 224u) & 255u;
+                const unsigned vr = (vg + (rb >> 4) + 248u) & 255u, vb = (vg + (rb & 15u) + 248u) & 255u;
+                o.data = vr | vg << 8 | vb << 16;
+                o.lin  = __dp4a(o.data, 0x00070503u, 0u) & 63u;
+            } else {
+                o.kind = K_RUN, o.npix = (tag & 63u) + 1u;  // simple.cpp:156-163
+            }
+        }
+        return o;
+    }
+
+    __device__ __forceinline__ Seg op_seg(const OpInfo& o, unsigned p)
+    {
+        Seg s;
+        s.cnt = o.npix | 1u << 20;
+        s.da = 0, s.fl = 0;
+        switch (o.kind) {
+        case K_RGB: s.fl = p | o.lin << 16 | kFlRoot | kFlUses; break;
+        case K_RGBA: s.fl = p | o.lin << 16 | kFlRoot | kFlRgba, s.da = o.data & 0xFF000000u; break;
+        case K_INDEX: s.fl = p | o.lin << 16 | kFlRoot; break;
+        case K_DIFF:
+        case K_LUMA: s.da = o.data, s.fl = o.lin << 16; break;
+        default: break;
+        }
+        return s;
+    }
+
+    __device__ __forceinline__ Seg seg_shfl_up(const Seg& s, unsigned d)
+    {
+        return Seg{ __shfl_up_sync(kFull, s.cnt, d), __shfl_up_sync(kFull, s.da, d), __shfl_up_sync(kFull, s.fl, d) };
+    }
+
+    // store one pixel (target 3 or 4 bytes), optionally bottom-up rows (simple.cpp:401-408 done in place)
+    __device__ __forceinline__ void store_pixel(uint8_t* out, uint64_t pix, unsigned val, const DecParams& P)
+    {
+        if (P.flip) {
+            const uint64_t y = pix / P.width, x = pix - y * P.width;
+            pix = (uint64_t)(P.height - 1 - y) * P.width + x;
+        }
+        if (P.target == 4) {
+            uint8_t* d = out + pix * 4;
+            if ((reinterpret_cast<uintptr_t>(out) & 3u) == 0) *reinterpret_cast<unsigned*>(d) = val;
+            else d[0] = (uint8_t)val, d[1] = (uint8_t)(val >> 8), d[2] = (uint8_t)(val >> 16), d[3] = (uint8_t)(val >> 24);
+        } else {
+            uint8_t* d = out + pix * 3;
+            d[0] = (uint8_t)val, d[1] = (uint8_t)(val >> 8), d[2] = (uint8_t)(val >> 16);
+        }
+    }
+
+    __device__ __forceinline__ void locate_image(const DecParams& P, unsigned gt, unsigned& img, unsigned& t, unsigned& ntiles,
+                                                 const uint8_t*& stream, uint64_t& size)
+    {
+        if (P.tile_first == nullptr) {
+            img = 0, t = gt, ntiles = P.n_tiles;
+            stream = P.qoi + P.single[0], size = P.single[1] - P.single[0];
+            return;
+        }
+        unsigned lo = 0, hi = P.n_images;  // largest img with tile_first[img] <= gt
+        while (hi - lo > 1) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (__ldg(P.tile_first + mid) <= gt) lo = mid;
+            else hi = mid;
+        }
+        img    = lo;
+        const unsigned f = __ldg(P.tile_first + lo);
+        t = gt - f, ntiles = __ldg(P.tile_first + lo + 1) - f;
+        const uint64_t o0 = __ldg(P.offsets + lo);
+        stream = P.qoi + o0, size = __ldg(P.offsets + lo + 1) - o0;
+    }
+
+    __global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecParams P)
+    {
+        DecSmem&       sm  = *reinterpret_cast<DecSmem*>(QB_DYN_SMEM);
+        const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+
+        if (tid == 0) {
+            sm.ticket  = atomicInc(P.ticket, P.n_tiles - 1u);
+            sm.bad     = 0;
+            sm.changed = 0;
+        }
+        __syncthreads();
+        unsigned       img, t, ntiles;
+        const uint8_t* stream;
+        uint64_t       size;
+        locate_image(P, sm.ticket, img, t, ntiles, stream, size);
+        const uint64_t body_len = size - kHeader;  // every byte after the header is chunk data (simple.cpp:110-113)
+        const uint64_t tile_b0  = (uint64_t)t * kDecTB;
+        const unsigned limit    = (unsigned)(body_len - tile_b0 < (uint64_t)kDecTB ? body_len - tile_b0 : (uint64_t)kDecTB);
+        uint64_t*      desc     = P.desc + (uint64_t)sm.ticket * kDecDescWords;
+        const unsigned epoch    = P.epoch;
+        uint8_t*       out      = P.out + (uint64_t)img * P.out_stride;
+        const uint64_t N        = P.n_pixels;
+        DecResult*     res      = P.results + img;
+
+        // ---- stage the tile: 16-byte aligned chunks land at the same misalignment in shared memory
+        const uint8_t* src   = stream + kHeader + tile_b0;
+        const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+        {
+            const uint64_t avail = body_len - tile_b0;  // bytes of the stream from the tile start
+            const unsigned want  = (unsigned)(avail < (uint64_t)(kDecTB + 8) ? avail : (uint64_t)(kDecTB + 8));
+            const unsigned nvec  = (shift + want + 15u) >> 4;
+            const uint4*   vsrc  = reinterpret_cast<const uint4*>(src - shift);
+            for (unsigned c = tid; c < nvec; c += kDecThreads) reinterpret_cast<uint4*>(sm.bytes)[c] = __ldg(vsrc + c);
+            __syncthreads();
+            for (unsigned b = shift + want + tid; b < kDecTB + 48; b += kDecThreads) sm.bytes[b] = 0;  // zero padding, simple.cpp:106
+            __syncthreads();
+        }
+        const unsigned char* B = sm.bytes + shift;
+
+        // ================= carry (1): parse map =================
+        unsigned mymap;
+        {
+            unsigned win = 0;  // exit offsets of positions j+1..j+5, 3 bits each
+#pragma unroll
+            for (int j = kDecSB - 1; j >= 0; --j) {
+                const unsigned L   = op_length(B[tid * kDecSB + j]);
+                const unsigned nxt = j + L;
+                const unsigned e   = nxt >= (unsigned)kDecSB ? nxt - kDecSB : (win >> (3u * (L - 1u))) & 7u;
+                win                = (win << 3 | e) & 0x7FFFu;
+            }
+            mymap = win;
+        }
+        unsigned incl_map = mymap;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(kFull, incl_map, d);
+            if ((int)lane >= d) incl_map = map_compose(o, incl_map);
+        }
+        if (lane == 31) sm.wmap[w] = incl_map;
+        __syncthreads();
+        unsigned excl_map = __shfl_up_sync(kFull, incl_map, 1);
+        if (lane == 0) excl_map = kMapIdentity;
+        {
+            unsigned wp = kMapIdentity;
+            for (unsigned ww = 0; ww < w; ++ww) wp = map_compose(wp, sm.wmap[ww]);
+            excl_map = map_compose(wp, excl_map);
+        }
+        if (tid == 0) {
+            unsigned tile_map = kMapIdentity;
+            for (unsigned ww = 0; ww < kDecWarps; ++ww) tile_map = map_compose(tile_map, sm.wmap[ww]);
+            unsigned entry = 0;
+            if (t > 0) {
+                st_word(desc + kDwParse, pack_word(tile_map, ST_AGG, epoch));
+                unsigned acc = kMapIdentity;
+                for (int p = (int)t - 1;; --p) {
+                    const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kDecDescWords + kDwParse, epoch);
+                    if (word_status(wd, epoch) == ST_INCL) {
+                        entry = (acc >> (3u * (unsigned)word_payload(wd))) & 7u;
+                        break;
+                    }
+                    acc = map_compose((unsigned)word_payload(wd), acc);
+                }
+            }
+            st_word(desc + kDwParse, pack_word((tile_map >> (3u * entry)) & 7u, ST_INCL, epoch));
+            sm.entry = entry;
+        }
+        __syncthreads();
+        const unsigned my_entry = (excl_map >> (3u * sm.entry)) & 7u;
+
+        // ================= carry (2): counts, slot / alpha =================
+        Seg mine = seg_identity();
+        walk_ops(B, tid, my_entry, limit, [&](unsigned p, unsigned tag) { mine = combine(mine, op_seg(op_info(B, p, tag), p)); });
+        Seg incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Seg o = seg_shfl_up(incl, d);
+            if ((int)lane >= d) incl = combine(o, incl);
+        }
+        if (lane == 31) sm.wseg[w] = incl;
+        __syncthreads();
+        Seg excl = seg_shfl_up(incl, 1);
+        if (lane == 0) excl = seg_identity();
+        {
+            Seg wp = seg_identity();
+            for (unsigned ww = 0; ww < w; ++ww) wp = combine(wp, sm.wseg[ww]);
+            excl = combine(wp, excl);
+        }
+        if (tid == 0 || tid == 32) {
+            Seg tot = seg_identity();
+            for (unsigned ww = 0; ww < kDecWarps; ++ww) tot = combine(tot, sm.wseg[ww]);
+            if (tid == 0) {  // pixels before this tile
+                const unsigned npix = tot.cnt & 0xFFFFFu;
+                sm.n_ops = tot.cnt >> 20, sm.n_pix = npix;
+                uint64_t base = 0;
+                if (t > 0) {
+                    st_word(desc + kDwPix, pack_word(npix, ST_AGG, epoch));
+                    for (int p = (int)t - 1;; --p) {
+                        const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kDecDescWords + kDwPix, epoch);
+                        base += word_payload(wd);
+                        if (word_status(wd, epoch) == ST_INCL) break;
+                    }
+                }
+                const uint64_t total = base + npix;
+                st_word(desc + kDwPix, pack_word(total < (1ull << 41) ? total : (1ull << 41), ST_INCL, epoch));
+                sm.pix_base = base;
+            } else {  // slot and alpha of the value entering the tile
+                // payload: c | root << 6 | uses << 7 | rgba << 8 | alpha << 9
+                auto pack = [](const Seg& s) {
+                    return ((s.fl >> 16) & 63u) | ((s.fl & kFlRoot) ? 64u : 0u) | ((s.fl & kFlUses) ? 128u : 0u) |
+                           ((s.fl & kFlRgba) ? 256u : 0u) | (s.da >> 24) << 9;
+                };
+                auto unpack = [](unsigned v) {
+                    return Seg{ 0u, (v >> 9) << 24, (v & 63u) << 16 | ((v & 64u) ? kFlRoot : 0u) | ((v & 128u) ? kFlUses : 0u) | ((v & 256u) ? kFlRgba : 0u) };
+                };
+                const Seg start = Seg{ 0u, 255u << 24, 53u << 16 | kFlRoot | kFlRgba };  // {0,0,0,255}: slot 53 (simple.cpp:108)
+                Seg       acc   = seg_identity();
+                if (t == 0) {
+                    acc = start;
+                } else {
+                    st_word(desc + kDwSlot, pack_word(pack(tot), ST_AGG, epoch));
+                    for (int p = (int)t - 1;; --p) {
+                        const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kDecDescWords + kDwSlot, epoch);
+                        acc               = combine(unpack((unsigned)word_payload(wd)), acc);
+                        if (word_status(wd, epoch) == ST_INCL) break;
+                    }
+                }
+                sm.slot_in  = (acc.fl >> 16) & 63u;  // concrete: the chain ended in an inclusive word
+                sm.alpha_in = acc.da >> 24;
+                const Seg o = combine(acc, tot);
+                st_word(desc + kDwSlot, pack_word(pack(o), ST_INCL, epoch));
+            }
+        }
+        __syncthreads();
+
+        // ================= per-op records (compact, stream order) =================
+        const unsigned n_ops = sm.n_ops;
+        {
+            const unsigned alpha_in = sm.alpha_in, slot_in = sm.slot_in;
+            unsigned k      = excl.cnt >> 20;
+            unsigned pixoff = excl.cnt & 0xFFFFFu;
+            unsigned alpha  = (excl.fl & kFlRgba) ? excl.da >> 24 : alpha_in;
+            unsigned slot   = (excl.fl & kFlRoot) ? (((excl.fl >> 16) & 63u) + ((excl.fl & kFlUses) ? 11u * alpha_in : 0u)) & 63u
+                                                  : (slot_in + ((excl.fl >> 16) & 63u)) & 63u;
+            unsigned root   = (excl.fl & kFlRoot) ? (excl.fl & 0xFFFFu) : kNoRoot;
+            unsigned delta  = excl.da & 0xFFFFFFu;
+            walk_ops(B, tid, my_entry, limit, [&](unsigned p, unsigned tag) {
+                const OpInfo o = op_info(B, p, tag);
+                switch (o.kind) {
+                case K_RGB: {
+                    const unsigned lit = o.data | alpha << 24;  // speculated alpha, verified below
+                    slot = slot_of(lit), root = p, delta = 0;
+                    sm.link[p] = (uint64_t)kPtrConst << 32 | lit;
+                } break;
+                case K_RGBA:
+                    alpha = o.data >> 24, slot = o.lin, root = p, delta = 0;
+                    sm.link[p] = (uint64_t)kPtrConst << 32 | o.data;
+                    break;
+                case K_INDEX: slot = o.lin, root = p, delta = 0; break;
+                case K_DIFF:
+                case K_LUMA: delta = add4(delta, o.data) & 0xFFFFFFu, slot = (slot + o.lin) & 63u; break;
+                default: break;
+                }
+                sm.op_pos[k]  = (unsigned short)p;
+                sm.op_root[k] = (unsigned short)root;
+                sm.op_val[k]  = delta;
+                sm.op_meta[k] = pixoff | (o.npix - 1u) << 17 | o.kind << 23 | slot << 26;
+                ++k, pixoff += o.npix;
+            });
+        }
+        sm.wtab[tid]               = (unsigned short)kNoOp;
+        sm.wtab[tid + kDecThreads] = (unsigned short)kNoOp;
+        __syncthreads();
+
+        // ================= writers of the INDEX ops =================
+        const unsigned per_warp = ((n_ops + kDecWarps * 32 - 1) / (kDecWarps * 32)) * 32;  // ops per warp, multiple of 32
+        const unsigned k0 = w * per_warp, k1 = min(k0 + per_warp, n_ops);
+        // value of colour op `wk` as a link: (its root's link) + its delta; roots before the tile hang off `prev`
+        auto link_of_op = [&](unsigned wk) -> uint64_t {
+            const unsigned r = sm.op_root[wk];
+            return (uint64_t)r << 32 | sm.op_val[wk];  // ptr = root position (or kNoRoot), add = delta; jumped below
+        };
+        for (unsigned kb = k0; kb < k1; kb += 32) {
+            const unsigned k      = kb + lane;
+            const bool     valid  = k < k1;
+            const unsigned meta   = valid ? sm.op_meta[k] : (K_RUN << 23);
+            const unsigned kind   = (meta >> 23) & 7u, slot = meta >> 26;
+            const bool     colour = kind != K_RUN;
+            const unsigned m      = __match_any_sync(kFull, colour ? slot : 64u + lane);
+            const unsigned below  = m & lanemask_lt(lane);
+            const unsigned prevw  = sm.wtab[w * 64 + slot];
+            if (kind == K_INDEX && valid) {
+                const unsigned wk = below ? kb + (31u - __clz(below)) : prevw;
+                // unresolved inside the warp: remember "look in earlier warps" as ptr = kPtrLeafSlot + slot (fixed below)
+                sm.link[sm.op_pos[k]] = wk != kNoOp ? link_of_op(wk) : (uint64_t)(kPtrLeafSlot + slot) << 32;
+            }
+            __syncwarp();
+            if (colour && (m & lanemask_gt(lane)) == 0) sm.wtab[w * 64 + slot] = (unsigned short)k;
+            __syncwarp();
+        }
+        __syncthreads();
+        // INDEX ops whose writer lies in an earlier warp of this tile
+        for (unsigned kb = k0; kb < k1; kb += 32) {
+            const unsigned k = kb + lane;
+            if (k < k1) {
+                const unsigned meta = sm.op_meta[k];
+                if (((meta >> 23) & 7u) == K_INDEX) {
+                    const unsigned p = sm.op_pos[k];
+                    if ((unsigned)(sm.link[p] >> 32) == kPtrLeafSlot + (meta >> 26)) {
+                        for (int ww = (int)w - 1; ww >= 0; --ww) {
+                            const unsigned wk = sm.wtab[ww * 64 + (meta >> 26)];
+                            if (wk != kNoOp) { sm.link[p] = link_of_op(wk); break; }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= collapse INDEX -> INDEX chains (pointer jumping; 64-bit links are read/written whole) =================
+        // a link's ptr is: a root position (< kPtrConst) still to be followed, kNoRoot (= value entering the tile as prev),
+        // kPtrConst, kPtrLeafSlot + s or kPtrLeafPrev
+        for (;;) {
+            bool changed = false;
+            for (unsigned k = tid; k < n_ops; k += kDecThreads) {
+                if (((sm.op_meta[k] >> 23) & 7u) != K_INDEX) continue;
+                const unsigned p = sm.op_pos[k];
+                uint64_t       L = sm.link[p];
+                unsigned       ptr = (unsigned)(L >> 32);
+                if (ptr == kNoRoot) {
+                    sm.link[p] = (uint64_t)kPtrLeafPrev << 32 | (unsigned)L;
+                } else if (ptr < kPtrConst) {
+                    const uint64_t Tl   = sm.link[ptr];
+                    const unsigned tptr = (unsigned)(Tl >> 32);
+                    // the target root's own link may itself still point at a root: follow again next round
+                    sm.link[p] = (uint64_t)(tptr == kNoRoot ? kPtrLeafPrev : tptr) << 32 | add4((unsigned)L, (unsigned)Tl);
+                    changed    = true;
+                }
+            }
+            if (!__syncthreads_or(changed)) break;
+        }
+
+        // ================= carry (3): the tile's transfer function, look-back, concrete state =================
+        if (tid < 65) {
+            // outgoing entry e: table slot e (< 64) or prev (64)
+            unsigned wk = kNoOp;
+            if (tid < 64) {
+                for (int ww = kDecWarps - 1; ww >= 0; --ww) {
+                    const unsigned x = sm.wtab[ww * 64 + tid];
+                    if (x != kNoOp) { wk = x; break; }
+                }
+            } else if (n_ops) {
+                wk = n_ops - 1;
+            }
+            unsigned code = tid == 64 ? kPtrLeafPrev : kPtrLeafSlot + tid, add = 0;
+            if (wk != kNoOp) {
+                const unsigned r = sm.op_root[wk];
+                add              = sm.op_val[wk];
+                if (r == kNoRoot) code = kPtrLeafPrev;
+                else {
+                    const uint64_t L = sm.link[r];
+                    code = (unsigned)(L >> 32), add = add4(add, (unsigned)L);
+                }
+            }
+            sm.fn_code[tid] = code, sm.fn_add[tid] = add;
+            // payload: add | entry code << 32 (0..63 slot, 64 prev, 65 constant)
+            auto enc = [](unsigned c) { return c == kPtrConst ? 65u : (c == kPtrLeafPrev ? 64u : c - kPtrLeafSlot); };
+            if (code != kPtrConst) st_word(desc + kDwState + tid, pack_word((uint64_t)enc(code) << 32 | add, ST_AGG, epoch));
+            else st_word(desc + kDwState + tid, pack_word(add, ST_INCL, epoch));  // a constant is already inclusive
+            // incoming value of entry `tid`: follow the chain through the predecessors
+            unsigned e = tid, acc = 0, v;
+            for (int p = (int)t - 1;; --p) {
+                if (p < 0) {  // simple.cpp:103-108: zero table, prev = start, start stored at its slot
+                    v = add4((e == 64 || e == 53) ? kStartPixel : 0u, acc);
+                    break;
+                }
+                const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kDecDescWords + kDwState + e, epoch);
+                const uint64_t pl = word_payload(wd);
+                if (word_status(wd, epoch) == ST_INCL) { v = add4((unsigned)pl, acc); break; }
+                acc = add4(acc, (unsigned)pl);
+                const unsigned c = (unsigned)(pl >> 32);
+                if (c == 65u) { v = acc; break; }
+                e = c;
+            }
+            sm.in_state[tid] = v;
+        }
+        __syncthreads();
+        if (tid < 65) {
+            const unsigned code = sm.fn_code[tid], add = sm.fn_add[tid];
+            const unsigned v    = code == kPtrConst ? add : add4(sm.in_state[code == kPtrLeafPrev ? 64 : code - kPtrLeafSlot], add);
+            st_word(desc + kDwState + tid, pack_word(v, ST_INCL, epoch));
+            sm.fn_add[tid] = v;  // concrete outgoing state
+        }
+
+        // ================= values, verification, pixels =================
+        for (unsigned k = tid; k < n_ops; k += kDecThreads) {
+            const unsigned r = sm.op_root[k];
+            unsigned       base;
+            if (r == kNoRoot) base = sm.in_state[64];
+            else {
+                const uint64_t L   = sm.link[r];
+                const unsigned ptr = (unsigned)(L >> 32);
+                base = ptr == kPtrConst ? (unsigned)L : add4(sm.in_state[ptr == kPtrLeafPrev ? 64 : ptr - kPtrLeafSlot], (unsigned)L);
+            }
+            sm.op_val[k] = add4(base, sm.op_val[k]);
+        }
+        __syncthreads();
+        const uint64_t pix_base = sm.pix_base;
+        bool           bad      = false;
+        for (unsigned k = tid; k < n_ops; k += kDecThreads) {
+            const unsigned meta = sm.op_meta[k], kind = (meta >> 23) & 7u, val = sm.op_val[k];
+            const uint64_t pix = pix_base + (meta & 0x1FFFFu);
+            if (pix < N) {  // ops past the image are never executed by the reference
+                if (kind == K_RGB) bad |= (val >> 24) != ((k ? sm.op_val[k - 1] : sm.in_state[64]) >> 24);  // simple.cpp:119-123
+                if (kind == K_INDEX) bad |= slot_of(val) != (meta >> 26);  // a never-written slot was read
+            }
+            const unsigned np  = ((meta >> 17) & 63u) + 1u;
+            for (unsigned j = 0; j < np && pix + j < N; ++j) store_pixel(out, pix + j, val, P);
+        }
+        if (bad) sm.bad = 1;
+        __syncthreads();
+        if (tid == 0 && sm.bad) atomicOr(&res->bad, 1u);
+
+        // ---- the stream ended before the image: the zero padding decodes as INDEX 0 forever (simple.cpp:106,132-135)
+        if (t == ntiles - 1) {
+            const uint64_t have = pix_base + sm.n_pix;
+            const unsigned fill = sm.fn_add[0];
+            if (tid == 0) {
+                res->pixels = have < N ? have : N;
+                if (have < N && slot_of(fill) != 0) atomicOr(&res->bad, 1u);
+            }
+            for (uint64_t pix = have + tid; pix < N; pix += kDecThreads) store_pixel(out, pix, fill, P);
+        }
+    }
+
+    // =====================================================================================================
+    // Exact sequential decoder: the reference loop (simple.cpp:100-171, stream.cpp:312-447) with one decoding lane per
+    // image; the other 31 lanes stage input and output through shared memory.  Runs only when `bad` is set
+    // (mode 0), or always for the resumable entry point (mode 1) whose buffers are small by construction.
+    // =====================================================================================================
+    struct SerialParams {
+        DecParams       d;
+        uint32_t        mode;      // 0 = redo images flagged bad; 1 = resumable decode of one buffer
+        const DecState* init;      // mode 1 carry-in
+        uint64_t        in_size;   // mode 1: bytes available (no header), out capacity in bytes is d.out_stride
+    };
+
+    constexpr int kSerIn = 4096, kSerOut = 1024;
+    struct SerialSmem {
+        unsigned char in[kSerIn + 16];
+        unsigned      px[kSerOut];
+        unsigned      table[64];
+        unsigned      ctl[8];
+    };
+
+    __global__ void __launch_bounds__(32) decode_serial_kernel(const SerialParams S)
+    {
+        SerialSmem&           sm   = *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM);
+        const DecParams&      P    = S.d;
+        const unsigned        lane = threadIdx.x;
+        const unsigned        img  = blockIdx.x;
+        DecResult*            res  = P.results + img;
+        if (S.mode == 0 && res->bad == 0) return;
+
+        const uint8_t* stream;
+        uint64_t       size;
+        if (P.tile_first == nullptr) stream = P.qoi + P.single[0], size = P.single[1] - P.single[0];
+        else stream = P.qoi + P.offsets[img], size = P.offsets[img + 1] - P.offsets[img];
+        uint8_t*       out   = P.out + (uint64_t)img * (S.mode == 0 ? P.out_stride : 0);
+        const uint8_t* body  = S.mode == 0 ? stream + kHeader : stream;
+        const uint64_t blen  = S.mode == 0 ? size - kHeader : S.in_size;
+        const uint64_t room  = S.mode == 0 ? P.n_pixels : P.out_stride / P.target;  // pixels that may be produced
+
+        sm.table[lane] = 0, sm.table[lane + 32] = 0;
+        __syncwarp();
+        unsigned prev = kStartPixel, run = 0;
+        if (S.mode == 1) {
+            prev = S.init->prev, run = S.init->run;
+            sm.table[lane] = S.init->table[lane], sm.table[lane + 32] = S.init->table[lane + 32];
+        } else if (lane == 0) {
+            sm.table[53] = kStartPixel;  // simple.cpp:108
+        }
+        __syncwarp();
+
+        uint64_t pos = 0, px = 0;  // consumed input bytes, produced pixels
+        bool     stop = false;
+        while (!stop && px < room) {
+            // stage kSerIn bytes from `pos` (zero padded in mode 0)
+            for (unsigned b = lane; b < kSerIn + 8; b += 32) sm.in[b] = pos + b < blen ? body[pos + b] : 0;
+            __syncwarp();
+            if (lane == 0) {
+                unsigned ip = 0, op = 0;
+                while (op < kSerOut && px + op < room) {
+                    if (run) {  // pending run (stream.cpp:335-339)
+                        --run, sm.px[op++] = prev;
+                        continue;
+                    }
+                    if (ip >= kSerIn) break;
+                    if (S.mode == 1 && pos + ip >= blen) { stop = true; break; }  // stream.cpp:341-344
+                    const unsigned tag = sm.in[ip], len = op_length(tag);
+                    if (S.mode == 1 && pos + ip + len > blen) { stop = true; break; }  // incomplete op is not consumed
+                    const OpInfo o = op_info(sm.in, ip, tag);
+                    unsigned     cur = prev;
+                    switch (o.kind) {
+                    case K_RGB: cur = o.data | (prev & 0xFF000000u); break;
+                    case K_RGBA: cur = o.data; break;
+                    case K_INDEX: cur = sm.table[o.lin]; break;
+                    case K_DIFF:
+                    case K_LUMA: cur = add4(prev, o.data); break;
+                    default: run = o.npix - 1; break;  // RUN: one pixel now, the rest pending
+                    }
+                    ip += len;
+                    sm.px[op++] = cur;
+                    if (o.kind != K_RUN) sm.table[slot_of(cur)] = cur;  // simple.cpp:169
+                    prev = cur;
+                }
+                sm.ctl[0] = ip, sm.ctl[1] = op, sm.ctl[2] = stop;
+            }
+            __syncwarp();
+            const unsigned ip = sm.ctl[0], op = sm.ctl[1];
+            stop = sm.ctl[2] != 0;
+            for (unsigned j = lane; j < op; j += 32) store_pixel(out, px + j, sm.px[j], P);
+            __syncwarp();
+            pos += ip, px += op;
+            if (ip == 0 && op == 0) break;
+        }
+        if (S.mode == 0) {
+            if (lane == 0) res->path = 1, res->pixels = px;
+            return;
+        }
+        // mode 1 carry-out.  A run that is still pending when the input of mode 0 ends is dropped by the clamp
+        // (simple.cpp:158); in mode 1 it stays in the state (stream.cpp:405-409).
+        prev = __shfl_sync(kFull, prev, 0), run = __shfl_sync(kFull, run, 0);
+        res->state.table[lane] = sm.table[lane], res->state.table[lane + 32] = sm.table[lane + 32];
+        if (lane == 0) {
+            res->state.prev = prev, res->state.run = run;
+            res->processed = pos, res->written = px * P.target, res->path = 1;
+        }
+    }
+
 #ifndef QB_EMU
-    inline cudaError_t dec_set_attrs() { return cudaSuccess; }
+    inline cudaError_t dec_set_attrs()
+    {
+        return cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+    }
 #endif
-}
+}  // namespace qb

@@ -3,6 +3,7 @@
 // tests/emu/Makefile into tests/emu/libqb_emu.so; never part of libqoipp_b200.so.
 #include "cuda_emu.h"
 
+#include "../../qoipp_b200/csrc/decode_kernel.cuh"
 #include "../../qoipp_b200/csrc/encode_kernel.cuh"
 #include "../../qoipp_b200/csrc/host_util.hpp"
 
@@ -80,6 +81,61 @@ extern "C"
         dispatch_encode(P, (int)ch, K, resident, seed);
         *processed = res.processed * ch;
         *written   = res.written;
+        unpack(res.state.prev, st->prev);
+        st->run = (uint8_t)res.state.run;
+        for (int s = 0; s < 64; ++s) unpack(res.state.table[s], st->seen[s]);
+        return 0;
+    }
+
+    // one-shot / batch decode.  offsets has n_images + 1 entries (streams include their headers).
+    // out_path[k]: 0 = the parallel kernel's pixels stand, 1 = the sequential kernel re-decoded image k.
+    int emu_decode(const uint8_t* qoi, const uint64_t* offsets, uint32_t n_images, uint32_t w, uint32_t h, uint8_t target,
+                   int flip, uint8_t* out, uint64_t out_stride, int* out_path, int force_serial, int resident, uint64_t seed)
+    {
+        std::vector<uint32_t> tile_first(n_images + 1);
+        uint64_t              tiles = 0;
+        for (uint32_t k = 0; k < n_images; ++k) {
+            tile_first[k] = (uint32_t)tiles;
+            tiles += (offsets[k + 1] - offsets[k] - host::kHeaderSize + kDecTB - 1) / kDecTB;
+        }
+        tile_first[n_images] = (uint32_t)tiles;
+        DecParams P{};
+        P.qoi = qoi;
+        if (n_images == 1) { P.offsets = nullptr; P.tile_first = nullptr; P.single[0] = offsets[0]; P.single[1] = offsets[1]; }
+        else { P.offsets = offsets; P.tile_first = tile_first.data(); }
+        P.out = out; P.out_stride = out_stride; P.n_pixels = (uint64_t)w * h;
+        P.width = w; P.height = h; P.target = target; P.flip = flip;
+        P.n_images = n_images; P.n_tiles = (uint32_t)tiles; P.epoch = 3;
+        std::vector<uint64_t>  desc((size_t)tiles * kDecDescWords, 0);
+        std::vector<DecResult> res(n_images);
+        memset(res.data(), 0, sizeof(DecResult) * n_images);
+        uint32_t ticket = 0;
+        P.desc = desc.data(); P.results = res.data(); P.ticket = &ticket;
+        if (!force_serial)
+            emu::launch(dim3(P.n_tiles), dim3(kDecThreads), sizeof(DecSmem) + 128, [=] { decode_kernel(P); }, resident, seed);
+        else
+            for (auto& r : res) r.bad = 1;
+        if (ticket != 0) return -1;
+        SerialParams S{};
+        S.d = P; S.mode = 0;
+        emu::launch(dim3(n_images), dim3(32), sizeof(SerialSmem) + 128, [=] { decode_serial_kernel(S); }, resident, seed);
+        for (uint32_t k = 0; k < n_images; ++k) out_path[k] = (int)res[k].path;
+        return 0;
+    }
+
+    int emu_stream_decode(qoipp_b200_state* st, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t cap,
+                          uint64_t* processed, uint64_t* written)
+    {
+        DecState is{};
+        is.prev = pack(st->prev); is.run = st->run;
+        for (int s = 0; s < 64; ++s) is.table[s] = pack(st->seen[s]);
+        DecResult    res{};
+        SerialParams S{};
+        S.d.qoi = in; S.d.single[0] = 0; S.d.single[1] = in_size; S.d.out = out; S.d.out_stride = cap;
+        S.d.target = st->channels; S.d.flip = 0; S.d.n_images = 1; S.d.results = &res;
+        S.mode = 1; S.init = &is; S.in_size = in_size;
+        emu::launch(dim3(1), dim3(32), sizeof(SerialSmem) + 128, [=] { decode_serial_kernel(S); }, 1, 0);
+        *processed = res.processed; *written = res.written;
         unpack(res.state.prev, st->prev);
         st->run = (uint8_t)res.state.run;
         for (int s = 0; s < 64; ++s) unpack(res.state.table[s], st->seen[s]);

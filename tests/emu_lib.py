@@ -107,3 +107,92 @@ class StreamEncoder:
         out[k: k + 8] = [0, 0, 0, 0, 0, 0, 0, 1]
         self.reset()
         return 0, need
+
+
+def _setup_decode():
+    L = lib()
+    L.emu_decode.argtypes = [u8p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, C.c_int, u8p, C.c_uint64,
+                             C.POINTER(C.c_int), C.c_int, C.c_int, C.c_uint64]
+    L.emu_stream_decode.argtypes = [C.POINTER(State), u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    return L
+
+
+def decode(qoi_list, w, h, target, flip=False, force_serial=False, resident=4, seed=0):
+    """Decode one or several streams of equal shape in one launch -> (list of pixel arrays, list of path flags)."""
+    if isinstance(qoi_list, np.ndarray):
+        qoi_list = [qoi_list]
+    L = _setup_decode()
+    n = len(qoi_list)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    pad = 3  # deliberately misaligned stream starts
+    blob = np.zeros(sum(q.size + pad for q in qoi_list) + 64, dtype=np.uint8)
+    pos = 1
+    starts = []
+    for i, q in enumerate(qoi_list):
+        blob[pos: pos + q.size] = q
+        starts.append(pos)
+        pos += q.size + pad
+    # batch offsets must be contiguous ranges [offsets[k], offsets[k+1]) -> lay the streams out back to back instead
+    blob2 = np.concatenate([np.zeros(1, np.uint8)] + [np.ascontiguousarray(q, dtype=np.uint8) for q in qoi_list] + [np.zeros(64, np.uint8)])
+    o = 1
+    for i, q in enumerate(qoi_list):
+        offs[i] = o
+        o += q.size
+    offs[n] = o
+    stride = w * h * target + 5
+    out = np.full(stride * n + 16, 0xAA, dtype=np.uint8)
+    path = (C.c_int * n)()
+    rc = L.emu_decode(_p(blob2), offs.ctypes.data_as(C.POINTER(C.c_uint64)), n, w, h, target, int(flip), _p(out), stride, path,
+                      int(force_serial), resident, seed)
+    assert rc == 0, rc
+    px = [out[i * stride: i * stride + w * h * target].copy() for i in range(n)]
+    for i in range(n):
+        assert np.all(out[i * stride + w * h * target: (i + 1) * stride] == 0xAA), "decode wrote past the image"
+    return px, [int(x) for x in path]
+
+
+class StreamDecoder:
+    def __init__(self):
+        self.s = State()
+        self.reset()
+
+    def reset(self):
+        C.memset(C.byref(self.s), 0, C.sizeof(self.s))
+        self.s.prev[3] = 255
+
+    def initialize(self, inp, target=0):
+        from oracle.pyoracle import Oracle  # header parsing is host code; reuse the checker's rule table here
+        if self.s.channels:
+            return 9, None
+        e, d = Oracle.read_header(inp)
+        if e:
+            return e, None
+        ch = target or d[2]
+        self.s.channels = self.s.target = ch
+        self.s.seen[53 * 4 + 3] = 255
+        return 0, (d[0], d[1], ch, d[3])
+
+    def decode(self, out, inp):
+        if not self.s.channels:
+            return 8, 0, 0
+        if out.size == 0:
+            return 1, 0, 0
+        if out.size < self.s.channels:
+            return 2, 0, 0
+        L = _setup_decode()
+        p, n = C.c_uint64(0), C.c_uint64(0)
+        inp = np.ascontiguousarray(inp)
+        L.emu_stream_decode(C.byref(self.s), _p(inp) if inp.size else _p(np.zeros(1, np.uint8)), inp.size, _p(out), out.size,
+                            C.byref(p), C.byref(n))
+        return 0, p.value, n.value
+
+    def has_run_count(self):
+        return self.s.run > 0
+
+    def drain_run(self, out):
+        ch = self.s.channels
+        k = min(self.s.run, out.size // ch)
+        px = np.frombuffer(bytes(self.s.prev), dtype=np.uint8)[:ch]
+        out[: k * ch] = np.tile(px, k)
+        self.s.run -= k
+        return 0, k * ch

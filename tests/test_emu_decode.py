@@ -1,0 +1,156 @@
+"""CPU: the product DECODE kernels (qoipp_b200/csrc/decode_kernel.cuh) stepped by the SIMT emulator and compared
+with the oracle / the committed outputs of the unmodified reference."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import Oracle
+from qoipp_b200 import synth
+from tests import emu_lib as E
+from tests import helpers as H
+
+FX = H.fixtures()
+SIZES = [(1, 1), (1, 2), (1, 61), (1, 62), (1, 63), (1, 124), (29, 17), (24, 14), (255, 3), (100, 41)]
+
+
+def check(qoi, w, h, src_ch, target=0, flip=False, expect_path=None, **kw):
+    tgt = target or src_ch
+    ref = Oracle.decode(qoi, tgt, flip)
+    px, path = E.decode(qoi, w, h, tgt, flip=flip, **kw)
+    if not np.array_equal(px[0], ref):
+        bad = int(np.nonzero(px[0] != ref)[0][0]) // tgt
+        raise AssertionError(f"{w}x{h} src {src_ch} -> {tgt} flip={flip}: first wrong pixel {bad} (path {path})")
+    if expect_path is not None:
+        assert path[0] == expect_path
+    return path[0]
+
+
+@pytest.mark.parametrize("ch", [3, 4])
+def test_fixtures(ch):  # simple_test.cpp:179-223, 316-322
+    f = FX[ch]
+    w, h, _, _ = f["desc"]
+    for target in (0, 3, 4):
+        px, path = E.decode(f["qoi"], w, h, target or ch)
+        assert np.array_equal(px[0], H.retarget(f["raw"], ch, target))
+    check(f["qoi_incomplete"], w, h, ch)  # truncated: decodes the zero padding exactly like the reference
+
+
+@pytest.mark.parametrize("kind", synth.CLASSES)
+def test_classes_and_sizes(kind):
+    for ch in (3, 4):
+        for i, (w, h) in enumerate(SIZES):
+            raw = synth.generate(kind, w, h, ch)
+            q = Oracle.encode(raw, w, h, ch)
+            check(q, w, h, ch, target=[0, 3, 4][i % 3], flip=bool(i & 1), seed=i)
+
+
+@pytest.mark.parametrize("kind", ["photo", "dither", "palette", "noise", "resync", "gradient", "long_runs"])
+def test_opaque_content_stays_on_the_parallel_path(kind):
+    for ch in (3, 4):
+        w, h = 160, 100
+        raw = synth.generate(kind, w, h, ch)
+        if ch == 4:
+            raw = raw.copy()
+            raw[3::4] = 255
+        q = Oracle.encode(raw, w, h, ch)
+        for seed, resident in ((0, 1), (2, 3), (5, 8)):
+            check(q, w, h, ch, seed=seed, resident=resident, expect_path=0)
+
+
+def test_truncated_and_padded_streams():
+    for kind in ("photo", "palette", "long_runs"):
+        for ch in (3, 4):
+            w, h = 64, 37
+            raw = synth.generate(kind, w, h, ch)
+            q = Oracle.encode(raw, w, h, ch)
+            for cut in (q.size - 8, q.size - 9, q.size - 11, q.size // 2, 40, 23):
+                if cut > 22:
+                    check(q[:cut], w, h, ch)
+
+
+def test_committed_adversarial_streams():
+    v = H.ref_vectors()
+    n = 0
+    for k in v.keys():
+        parts = k.split("/")
+        if parts[0] == "adv" and parts[2] == "in":
+            name = parts[1]
+            q = v[k]
+            target = int(v[f"adv/{name}/target"][0])
+            e, (w, h, ch, cs) = Oracle.read_header(q)
+            assert e == 0
+            tgt = target or ch
+            px, path = E.decode(q, w, h, tgt)
+            assert np.array_equal(px[0], v[f"adv/{name}/out"]), (name, path)
+            n += 1
+    assert n >= 39
+
+
+def test_random_op_soup():
+    rng = np.random.default_rng(99)
+    tags = np.array([0, 1, 5, 53, 0x6A, 0x55, 0x7F, 0xA0, 0x88, 0x11, 0xC1, 0xC5, 38, 17, 0xFE, 0xFF, 0x80, 0x3F], dtype=np.uint8)
+    for it in range(60):
+        nb = int(rng.integers(1, 5000))
+        body = rng.choice(tags, size=nb) if it % 2 else rng.integers(0, 256, size=nb, dtype=np.uint8)
+        ch = 3 + (it & 1)
+        w, h = 97, int(rng.integers(1, 80))
+        hdr = np.frombuffer(b"qoif" + w.to_bytes(4, "big") + h.to_bytes(4, "big") + bytes([ch, 0]), dtype=np.uint8)
+        q = np.concatenate([hdr, body.astype(np.uint8), np.array([0, 0, 0, 0, 0, 0, 0, 1], np.uint8)])
+        check(q, w, h, ch, target=[0, 3, 4][it % 3], seed=it)
+
+
+def test_forced_sequential_kernel():
+    for kind in ("photo", "hash_collide", "alpha_toggle"):
+        for ch in (3, 4):
+            w, h = 80, 45
+            raw = synth.generate(kind, w, h, ch)
+            q = Oracle.encode(raw, w, h, ch)
+            for target in (3, 4):
+                check(q, w, h, ch, target=target, flip=True, force_serial=True, expect_path=1)
+
+
+def test_batch_decode():
+    w, h, ch = 40, 30, 4
+    raws = [synth.generate(["photo", "palette", "hash_collide", "noise", "flat"][k % 5], w, h, ch, seed=100 + k) for k in range(9)]
+    qs = [Oracle.encode(r, w, h, ch) for r in raws]
+    px, path = E.decode(qs, w, h, 4, seed=4)
+    for k in range(9):
+        assert np.array_equal(px[k], raws[k]), (k, path)
+    px, path = E.decode(qs, w, h, 3, seed=5)
+    for k in range(9):
+        assert np.array_equal(px[k], H.to_rgb(raws[k])), (k, path)
+
+
+@pytest.mark.parametrize("ch", [3, 4])
+def test_stream_decoder_sweep(ch):  # stream_test.cpp:204-252 (subset of sizes; the GPU test runs them all)
+    f = FX[ch]
+    dec = E.StreamDecoder()
+    for size in list(range(5, 40)) + list(range(40, 1025, 29)):
+        for target in (0, 3, 4):
+            px, desc = H.stream_decode(dec, size, f["qoi"], target)
+            assert np.array_equal(px, H.retarget(f["raw"], ch, target)), (size, target)
+        px, _ = H.stream_decode(dec, size, f["qoi_incomplete"])
+        assert px.size != f["raw"].size and np.array_equal(px, f["raw"][: px.size]), size
+
+
+def test_stream_decoder_state_by_state():
+    rng = np.random.default_rng(8)
+    for it in range(30):
+        kind = synth.CLASSES[it % len(synth.CLASSES)]
+        ch = 3 + (it & 1)
+        w, h = int(rng.integers(1, 60)), int(rng.integers(1, 40))
+        raw = synth.generate(kind, w, h, ch, seed=300 + it)
+        q = Oracle.encode(raw, w, h, ch)
+        a, b = E.StreamDecoder(), Oracle.StreamDecoder()
+        tgt = [0, 3, 4][it % 3]
+        assert a.initialize(q[:14], tgt)[0] == 0 and b.initialize(q[:14], tgt)[0] == 0
+        off = 14
+        for _ in range(10000):
+            if off >= q.size:
+                break
+            cap, take = int(rng.integers(4, 300)), int(rng.integers(1, 200))
+            oa, ob = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+            ra, rb = a.decode(oa, q[off: off + take]), b.decode(ob, q[off: off + take])
+            assert ra == rb, (kind, ch, off, cap, take, ra, rb)
+            assert np.array_equal(oa[: ra[2]], ob[: rb[2]])
+            assert a.s.run == b.s.run and bytes(a.s.prev) == bytes(b.s.prev) and bytes(a.s.seen) == bytes(b.s.seen)
+            off += ra[1]
