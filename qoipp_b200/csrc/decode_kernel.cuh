@@ -63,7 +63,6 @@ namespace qb
     constexpr int kDecThreads = 256, kDecWarps = 8, kDecSB = 8, kDecTB = kDecThreads * kDecSB;
     constexpr int kDecDescWords = 72;
     constexpr int kDwParse = 0, kDwPix = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
-    constexpr unsigned kMapIdentity = 0u | 1u << 3 | 2u << 6 | 3u << 9 | 4u << 12;
 
     // link / transfer-function entry codes
     constexpr unsigned kPtrConst = 0xFE00u, kPtrLeafSlot = 0xFF00u, kPtrLeafPrev = 0xFF40u, kNoRoot = 0xFFFFu, kNoOp = 0xFFFFu;
@@ -100,12 +99,66 @@ namespace qb
         return C;
     }
 
-    __device__ __forceinline__ unsigned map_compose(unsigned f, unsigned g)  // f first, then g
+    // parse map of a byte range: exit offset for each of the five possible entry offsets.  Entries 0..3 live in the
+    // bytes of `lo`, entry 4 in `hi`, so that composing two maps is two PRMT instructions.
+    struct Map {
+        unsigned lo, hi;
+    };
+    __device__ __forceinline__ Map map_identity() { return Map{ 0x03020100u, 4u }; }
+    __device__ __forceinline__ Map map_const(unsigned e) { return Map{ e * 0x01010101u, e }; }
+    __device__ __forceinline__ Map map_compose(const Map& f, const Map& g)  // f first, then g
     {
-        unsigned r = 0;
+        const unsigned sel = (f.lo & 7u) | ((f.lo >> 4) & 0x70u) | ((f.lo >> 8) & 0x700u) | ((f.lo >> 12) & 0x7000u);
+        return Map{ __byte_perm(g.lo, g.hi, sel), __byte_perm(g.lo, g.hi, f.hi & 7u) & 0xFFu };
+    }
+    __device__ __forceinline__ unsigned map_at(const Map& f, unsigned e) { return e < 4u ? (f.lo >> (8u * e)) & 7u : f.hi & 7u; }
+    __device__ __forceinline__ unsigned map_pack(const Map& f)
+    {
+        return (f.lo & 7u) | ((f.lo >> 8) & 7u) << 3 | ((f.lo >> 16) & 7u) << 6 | ((f.lo >> 24) & 7u) << 9 | (f.hi & 7u) << 12;
+    }
+    __device__ __forceinline__ Map map_unpack(unsigned v)
+    {
+        return Map{ (v & 7u) | ((v >> 3) & 7u) << 8 | ((v >> 6) & 7u) << 16 | ((v >> 9) & 7u) << 24, (v >> 12) & 7u };
+    }
+
+    template <class T>
+    __device__ __forceinline__ T shfl_up_T(const T& v, unsigned d)
+    {
+        T        r;
+        unsigned a[sizeof(T) / 4];
+        __builtin_memcpy(a, &v, sizeof(T));
 #pragma unroll
-        for (int e = 0; e < 5; ++e) r |= ((g >> (3u * ((f >> (3 * e)) & 7u))) & 7u) << (3 * e);
+        for (unsigned i = 0; i < sizeof(T) / 4; ++i) a[i] = __shfl_up_sync(kFull, a[i], d);
+        __builtin_memcpy(&r, a, sizeof(T));
         return r;
+    }
+
+    // inclusive scan across the lanes of a warp, then across the (<= 8) warp totals kept in shared memory.
+    // Returns the exclusive prefix of the calling thread; `total` receives the fold over the whole CTA.
+    // Contains one __syncthreads().
+    template <class T, class Comb>
+    __device__ __forceinline__ T cta_exclusive_scan(const T& mine, T* wtot /* smem [kDecWarps] */, const T& identity, Comb comb, T& total)
+    {
+        const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+        T              incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const T o = shfl_up_T(incl, d);
+            if ((int)lane >= d) incl = comb(o, incl);
+        }
+        if (lane == 31) wtot[w] = incl;
+        __syncthreads();
+        T wv = lane < (unsigned)kDecWarps ? wtot[lane] : identity;  // every warp scans the warp totals redundantly
+#pragma unroll
+        for (int d = 1; d < kDecWarps; d <<= 1) {
+            const T o = shfl_up_T(wv, d);
+            if ((int)lane >= d) wv = comb(o, wv);
+        }
+        total         = shfl_T(wv, kDecWarps - 1);
+        const T wpre  = shfl_T(wv, (int)((w + 31u) & 31u));
+        T       excl  = shfl_up_T(incl, 1);
+        if (lane == 0) excl = identity;
+        return w ? comb(wpre, excl) : excl;
     }
 
     __device__ __forceinline__ unsigned op_length(unsigned tag)  // simple.cpp:118-165
@@ -123,7 +176,7 @@ namespace qb
         unsigned short wtab[kDecWarps * 64];           // per warp: op index of the last colour op per slot
         unsigned       in_state[65], fn_code[65], fn_add[65];
         Seg            wseg[kDecWarps];
-        unsigned       wmap[kDecWarps];
+        Map            wmap[kDecWarps];
         uint64_t       pix_base;
         unsigned       ticket, entry, slot_in, alpha_in, n_ops, n_pix, bad, changed;
     };
@@ -238,10 +291,11 @@ namespace qb
         stream = P.qoi + o0, size = __ldg(P.offsets + lo + 1) - o0;
     }
 
-    __global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecParams P)
+    __global__ void __launch_bounds__(kDecThreads, 5) decode_kernel(const DecParams P)
     {
         DecSmem&       sm  = *reinterpret_cast<DecSmem*>(QB_DYN_SMEM);
         const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+        [[maybe_unused]] const long long qb_t0 = QB_T0();
 
         if (tid == 0) {
             sm.ticket  = atomicInc(P.ticket, P.n_tiles - 1u);
@@ -277,8 +331,9 @@ namespace qb
         }
         const unsigned char* B = sm.bytes + shift;
 
+        QB_STAMP(desc, 68, 0, qb_t0);  // ticket + staging
         // ================= carry (1): parse map =================
-        unsigned mymap;
+        Map mymap;
         {
             unsigned win = 0;  // exit offsets of positions j+1..j+5, 3 bits each
 #pragma unroll
@@ -288,110 +343,89 @@ namespace qb
                 const unsigned e   = nxt >= (unsigned)kDecSB ? nxt - kDecSB : (win >> (3u * (L - 1u))) & 7u;
                 win                = (win << 3 | e) & 0x7FFFu;
             }
-            mymap = win;
+            mymap = map_unpack(win);
         }
-        unsigned incl_map = mymap;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned o = __shfl_up_sync(kFull, incl_map, d);
-            if ((int)lane >= d) incl_map = map_compose(o, incl_map);
-        }
-        if (lane == 31) sm.wmap[w] = incl_map;
-        __syncthreads();
-        unsigned excl_map = __shfl_up_sync(kFull, incl_map, 1);
-        if (lane == 0) excl_map = kMapIdentity;
-        {
-            unsigned wp = kMapIdentity;
-            for (unsigned ww = 0; ww < w; ++ww) wp = map_compose(wp, sm.wmap[ww]);
-            excl_map = map_compose(wp, excl_map);
-        }
-        if (tid == 0) {
-            unsigned tile_map = kMapIdentity;
-            for (unsigned ww = 0; ww < kDecWarps; ++ww) tile_map = map_compose(tile_map, sm.wmap[ww]);
-            unsigned entry = 0;
-            if (t > 0) {
-                st_word(desc + kDwParse, pack_word(tile_map, ST_AGG, epoch));
-                unsigned acc = kMapIdentity;
-                for (int p = (int)t - 1;; --p) {
-                    const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kDecDescWords + kDwParse, epoch);
-                    if (word_status(wd, epoch) == ST_INCL) {
-                        entry = (acc >> (3u * (unsigned)word_payload(wd))) & 7u;
-                        break;
-                    }
-                    acc = map_compose((unsigned)word_payload(wd), acc);
-                }
+        Map       tile_map;
+        const Map excl_map = cta_exclusive_scan(mymap, sm.wmap, map_identity(), [](const Map& a, const Map& b) { return map_compose(a, b); }, tile_map);
+        if (w == 0) {  // 32 predecessors per look-back round; an inclusive word is the constant map "exit offset"
+            if (lane == 0 && t > 0) st_word(desc + kDwParse, pack_word(map_pack(tile_map), ST_AGG, epoch));
+            const Map in = warp_lookback<Map>(
+                desc + kDwParse, t, kDecDescWords, epoch, map_const(0), map_identity(),
+                [](uint64_t pl) { return map_unpack((unsigned)pl); }, [](const Map& a, const Map& b) { return map_compose(a, b); });
+            const unsigned entry = in.lo & 7u;  // `in` is constant: every chain ended in an inclusive word
+            if (lane == 0) {
+                st_word(desc + kDwParse, pack_word(map_pack(map_const(map_at(tile_map, entry))), ST_INCL, epoch));
+                sm.entry = entry;
             }
-            st_word(desc + kDwParse, pack_word((tile_map >> (3u * entry)) & 7u, ST_INCL, epoch));
-            sm.entry = entry;
         }
         __syncthreads();
-        const unsigned my_entry = (excl_map >> (3u * sm.entry)) & 7u;
+        const unsigned my_entry = map_at(excl_map, sm.entry);
 
+        QB_STAMP(desc, 68, 1, qb_t0);  // parse maps + look-back 1
         // ================= carry (2): counts, slot / alpha =================
-        Seg mine = seg_identity();
-        walk_ops(B, tid, my_entry, limit, [&](unsigned p, unsigned tag) { mine = combine(mine, op_seg(op_info(B, p, tag), p)); });
-        Seg incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const Seg o = seg_shfl_up(incl, d);
-            if ((int)lane >= d) incl = combine(o, incl);
-        }
-        if (lane == 31) sm.wseg[w] = incl;
-        __syncthreads();
-        Seg excl = seg_shfl_up(incl, 1);
-        if (lane == 0) excl = seg_identity();
+        // one parse of the thread's ops: the decoded op is parked in link[p] (meta << 32 | data) for the record pass
+        Seg      mine   = seg_identity();
+        unsigned starts = 0;  // bit j: an op starts at byte j of this thread's sub-chunk
         {
-            Seg wp = seg_identity();
-            for (unsigned ww = 0; ww < w; ++ww) wp = combine(wp, sm.wseg[ww]);
-            excl = combine(wp, excl);
-        }
-        if (tid == 0 || tid == 32) {
-            Seg tot = seg_identity();
-            for (unsigned ww = 0; ww < kDecWarps; ++ww) tot = combine(tot, sm.wseg[ww]);
-            if (tid == 0) {  // pixels before this tile
-                const unsigned npix = tot.cnt & 0xFFFFFu;
-                sm.n_ops = tot.cnt >> 20, sm.n_pix = npix;
-                uint64_t base = 0;
-                if (t > 0) {
-                    st_word(desc + kDwPix, pack_word(npix, ST_AGG, epoch));
-                    for (int p = (int)t - 1;; --p) {
-                        const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kDecDescWords + kDwPix, epoch);
-                        base += word_payload(wd);
-                        if (word_status(wd, epoch) == ST_INCL) break;
-                    }
+            unsigned cnt = 0, delta = 0, c = 0, flags = 0, rootpos = 0, alpha = 0;
+            walk_ops(B, tid, my_entry, limit, [&](unsigned p, unsigned tag) {
+                const OpInfo o = op_info(B, p, tag);
+                starts |= 1u << (p & (kDecSB - 1));
+                sm.link[p] = (uint64_t)(o.kind | (o.npix - 1u) << 3 | o.lin << 9) << 32 | o.data;
+                cnt += o.npix | 1u << 20;
+                switch (o.kind) {
+                case K_RGB:  // slot needs the inherited alpha: resolved here if an OP_RGBA came earlier in this sub-chunk
+                    rootpos = p, delta = 0;
+                    if (flags & kFlRgba) c = o.lin + 11u * alpha, flags = kFlRoot | kFlRgba;
+                    else c = o.lin, flags = kFlRoot | kFlUses;
+                    break;
+                case K_RGBA: rootpos = p, delta = 0, c = o.lin, alpha = o.data >> 24, flags = kFlRoot | kFlRgba; break;
+                case K_INDEX: rootpos = p, delta = 0, c = o.lin, flags = kFlRoot | (flags & kFlRgba); break;
+                case K_DIFF:
+                case K_LUMA: delta = add4(delta, o.data), c += o.lin; break;
+                default: break;
                 }
+            });
+            mine.cnt = cnt;
+            mine.da  = (delta & 0xFFFFFFu) | alpha << 24;
+            mine.fl  = rootpos | (c & 63u) << 16 | flags;
+        }
+        Seg       tot;
+        const Seg excl = cta_exclusive_scan(mine, sm.wseg, seg_identity(), [](const Seg& a, const Seg& b) { return combine(a, b); }, tot);
+        if (w == 0) {  // pixels before this tile
+            const unsigned npix = tot.cnt & 0xFFFFFu;
+            if (lane == 0 && t > 0) st_word(desc + kDwPix, pack_word(npix, ST_AGG, epoch));
+            const uint64_t base = warp_lookback<uint64_t>(
+                desc + kDwPix, t, kDecDescWords, epoch, (uint64_t)0, (uint64_t)0, [](uint64_t pl) { return pl; },
+                [](uint64_t a, uint64_t b) { return a + b; });
+            if (lane == 0) {
                 const uint64_t total = base + npix;
                 st_word(desc + kDwPix, pack_word(total < (1ull << 41) ? total : (1ull << 41), ST_INCL, epoch));
-                sm.pix_base = base;
-            } else {  // slot and alpha of the value entering the tile
-                // payload: c | root << 6 | uses << 7 | rgba << 8 | alpha << 9
-                auto pack = [](const Seg& s) {
-                    return ((s.fl >> 16) & 63u) | ((s.fl & kFlRoot) ? 64u : 0u) | ((s.fl & kFlUses) ? 128u : 0u) |
-                           ((s.fl & kFlRgba) ? 256u : 0u) | (s.da >> 24) << 9;
-                };
-                auto unpack = [](unsigned v) {
-                    return Seg{ 0u, (v >> 9) << 24, (v & 63u) << 16 | ((v & 64u) ? kFlRoot : 0u) | ((v & 128u) ? kFlUses : 0u) | ((v & 256u) ? kFlRgba : 0u) };
-                };
-                const Seg start = Seg{ 0u, 255u << 24, 53u << 16 | kFlRoot | kFlRgba };  // {0,0,0,255}: slot 53 (simple.cpp:108)
-                Seg       acc   = seg_identity();
-                if (t == 0) {
-                    acc = start;
-                } else {
-                    st_word(desc + kDwSlot, pack_word(pack(tot), ST_AGG, epoch));
-                    for (int p = (int)t - 1;; --p) {
-                        const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kDecDescWords + kDwSlot, epoch);
-                        acc               = combine(unpack((unsigned)word_payload(wd)), acc);
-                        if (word_status(wd, epoch) == ST_INCL) break;
-                    }
-                }
+                sm.pix_base = base, sm.n_ops = tot.cnt >> 20, sm.n_pix = npix;
+            }
+        } else if (w == 1) {  // slot and alpha of the value entering the tile
+            // payload: c | root << 6 | uses << 7 | rgba << 8 | alpha << 9
+            auto pack = [](const Seg& q) {
+                return ((q.fl >> 16) & 63u) | ((q.fl & kFlRoot) ? 64u : 0u) | ((q.fl & kFlUses) ? 128u : 0u) |
+                       ((q.fl & kFlRgba) ? 256u : 0u) | (q.da >> 24) << 9;
+            };
+            auto unpack = [](uint64_t v64) {
+                const unsigned v = (unsigned)v64;
+                return Seg{ 0u, (v >> 9) << 24, (v & 63u) << 16 | ((v & 64u) ? kFlRoot : 0u) | ((v & 128u) ? kFlUses : 0u) | ((v & 256u) ? kFlRgba : 0u) };
+            };
+            const Seg start = Seg{ 0u, 255u << 24, 53u << 16 | kFlRoot | kFlRgba };  // {0,0,0,255}: slot 53 (simple.cpp:108)
+            if (lane == 0 && t > 0) st_word(desc + kDwSlot, pack_word(pack(tot), ST_AGG, epoch));
+            const Seg acc = warp_lookback<Seg>(desc + kDwSlot, t, kDecDescWords, epoch, start, seg_identity(), unpack,
+                                               [](const Seg& a, const Seg& b) { return combine(a, b); });
+            if (lane == 0) {
                 sm.slot_in  = (acc.fl >> 16) & 63u;  // concrete: the chain ended in an inclusive word
                 sm.alpha_in = acc.da >> 24;
-                const Seg o = combine(acc, tot);
-                st_word(desc + kDwSlot, pack_word(pack(o), ST_INCL, epoch));
+                st_word(desc + kDwSlot, pack_word(pack(combine(acc, tot)), ST_INCL, epoch));
             }
         }
         __syncthreads();
 
+        QB_STAMP(desc, 69, 0, qb_t0);  // walk + look-back 2
         // ================= per-op records (compact, stream order) =================
         const unsigned n_ops = sm.n_ops;
         {
@@ -403,34 +437,38 @@ namespace qb
                                                   : (slot_in + ((excl.fl >> 16) & 63u)) & 63u;
             unsigned root   = (excl.fl & kFlRoot) ? (excl.fl & 0xFFFFu) : kNoRoot;
             unsigned delta  = excl.da & 0xFFFFFFu;
-            walk_ops(B, tid, my_entry, limit, [&](unsigned p, unsigned tag) {
-                const OpInfo o = op_info(B, p, tag);
-                switch (o.kind) {
+            for (unsigned bits = starts; bits; bits &= bits - 1u) {
+                const unsigned p    = tid * kDecSB + (unsigned)__ffs((int)bits) - 1u;
+                const uint64_t L    = sm.link[p];
+                const unsigned meta = (unsigned)(L >> 32), data = (unsigned)L;
+                const unsigned kind = meta & 7u, npix1 = (meta >> 3) & 63u, lin = (meta >> 9) & 63u;
+                switch (kind) {
                 case K_RGB: {
-                    const unsigned lit = o.data | alpha << 24;  // speculated alpha, verified below
+                    const unsigned lit = data | alpha << 24;  // speculated alpha, verified below
                     slot = slot_of(lit), root = p, delta = 0;
                     sm.link[p] = (uint64_t)kPtrConst << 32 | lit;
                 } break;
                 case K_RGBA:
-                    alpha = o.data >> 24, slot = o.lin, root = p, delta = 0;
-                    sm.link[p] = (uint64_t)kPtrConst << 32 | o.data;
+                    alpha = data >> 24, slot = lin, root = p, delta = 0;
+                    sm.link[p] = (uint64_t)kPtrConst << 32 | data;
                     break;
-                case K_INDEX: slot = o.lin, root = p, delta = 0; break;
+                case K_INDEX: slot = lin, root = p, delta = 0; break;
                 case K_DIFF:
-                case K_LUMA: delta = add4(delta, o.data) & 0xFFFFFFu, slot = (slot + o.lin) & 63u; break;
+                case K_LUMA: delta = add4(delta, data) & 0xFFFFFFu, slot = (slot + lin) & 63u; break;
                 default: break;
                 }
                 sm.op_pos[k]  = (unsigned short)p;
                 sm.op_root[k] = (unsigned short)root;
                 sm.op_val[k]  = delta;
-                sm.op_meta[k] = pixoff | (o.npix - 1u) << 17 | o.kind << 23 | slot << 26;
-                ++k, pixoff += o.npix;
-            });
+                sm.op_meta[k] = pixoff | npix1 << 17 | kind << 23 | slot << 26;
+                ++k, pixoff += npix1 + 1u;
+            }
         }
         sm.wtab[tid]               = (unsigned short)kNoOp;
         sm.wtab[tid + kDecThreads] = (unsigned short)kNoOp;
         __syncthreads();
 
+        QB_STAMP(desc, 69, 1, qb_t0);  // records
         // ================= writers of the INDEX ops =================
         const unsigned per_warp = ((n_ops + kDecWarps * 32 - 1) / (kDecWarps * 32)) * 32;  // ops per warp, multiple of 32
         const unsigned k0 = w * per_warp, k1 = min(k0 + per_warp, n_ops);
@@ -476,6 +514,7 @@ namespace qb
         }
         __syncthreads();
 
+        QB_STAMP(desc, 70, 0, qb_t0);  // writers
         // ================= collapse INDEX -> INDEX chains (pointer jumping; 64-bit links are read/written whole) =================
         // a link's ptr is: a root position (< kPtrConst) still to be followed, kNoRoot (= value entering the tile as prev),
         // kPtrConst, kPtrLeafSlot + s or kPtrLeafPrev
@@ -499,6 +538,7 @@ namespace qb
             if (!__syncthreads_or(changed)) break;
         }
 
+        QB_STAMP(desc, 70, 1, qb_t0);  // pointer jumping
         // ================= carry (3): the tile's transfer function, look-back, concrete state =================
         if (tid < 65) {
             // outgoing entry e: table slot e (< 64) or prev (64)
@@ -551,6 +591,7 @@ namespace qb
             sm.fn_add[tid] = v;  // concrete outgoing state
         }
 
+        QB_STAMP(desc, 71, 0, qb_t0);  // state look-back
         // ================= values, verification, pixels =================
         for (unsigned k = tid; k < n_ops; k += kDecThreads) {
             const unsigned r = sm.op_root[k];
@@ -573,13 +614,18 @@ namespace qb
                 if (kind == K_RGB) bad |= (val >> 24) != ((k ? sm.op_val[k - 1] : sm.in_state[64]) >> 24);  // simple.cpp:119-123
                 if (kind == K_INDEX) bad |= slot_of(val) != (meta >> 26);  // a never-written slot was read
             }
-            const unsigned np  = ((meta >> 17) & 63u) + 1u;
-            for (unsigned j = 0; j < np && pix + j < N; ++j) store_pixel(out, pix + j, val, P);
+            const unsigned np1 = (meta >> 17) & 63u;
+            if (np1 == 0) {
+                if (pix < N) store_pixel(out, pix, val, P);
+            } else {
+                for (unsigned j = 0; j <= np1 && pix + j < N; ++j) store_pixel(out, pix + j, val, P);  // OP_RUN, clamped (simple.cpp:158)
+            }
         }
         if (bad) sm.bad = 1;
         __syncthreads();
         if (tid == 0 && sm.bad) atomicOr(&res->bad, 1u);
 
+        QB_STAMP(desc, 71, 1, qb_t0);  // values + stores
         // ---- the stream ended before the image: the zero padding decodes as INDEX 0 forever (simple.cpp:106,132-135)
         if (t == ntiles - 1) {
             const uint64_t have = pix_base + sm.n_pix;
@@ -700,7 +746,9 @@ namespace qb
 #ifndef QB_EMU
     inline cudaError_t dec_set_attrs()
     {
-        return cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+        cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
 #endif
 }  // namespace qb

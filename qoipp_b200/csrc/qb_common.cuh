@@ -77,6 +77,81 @@ namespace qb
         return w;
     }
 
+    // shuffles of trivially copyable values made of 32-bit words
+    template <class T>
+    __device__ __forceinline__ T shfl_down_T(const T& v, unsigned d)
+    {
+        static_assert(sizeof(T) % 4 == 0, "word multiple");
+        T        r;
+        unsigned a[sizeof(T) / 4];
+        __builtin_memcpy(a, &v, sizeof(T));
+#pragma unroll
+        for (unsigned i = 0; i < sizeof(T) / 4; ++i) a[i] = __shfl_down_sync(kFull, a[i], d);
+        __builtin_memcpy(&r, a, sizeof(T));
+        return r;
+    }
+    template <class T>
+    __device__ __forceinline__ T shfl_T(const T& v, int src)
+    {
+        static_assert(sizeof(T) % 4 == 0, "word multiple");
+        T        r;
+        unsigned a[sizeof(T) / 4];
+        __builtin_memcpy(a, &v, sizeof(T));
+#pragma unroll
+        for (unsigned i = 0; i < sizeof(T) / 4; ++i) a[i] = __shfl_sync(kFull, a[i], src);
+        __builtin_memcpy(&r, a, sizeof(T));
+        return r;
+    }
+
+    // ---- warp-cooperative decoupled look-back (all 32 lanes of ONE warp call this together)
+    // Lane l inspects predecessor base - l of tile t; words are `stride` uint64 apart, `w0` is tile t's own word.
+    // Status ST_AGG / ST_AGG_EMPTY carries the tile's own aggregate, ST_INCL the inclusive prefix; the virtual tile -1
+    // is inclusive with payload `init`.  Returns, in every lane, pred(t-1) (+) ... folded onto nothing, i.e. the exclusive
+    // prefix of tile t.  `comb(earlier, later)` must be associative; `empty` is its identity (used for ST_AGG_EMPTY too).
+    template <class T, class FromWord, class Comb>
+    __device__ __forceinline__ T warp_lookback(const uint64_t* w0, unsigned t, unsigned stride, unsigned epoch, T init, T empty,
+                                               FromWord from_word, Comb comb)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        T              acc  = empty;
+        for (int base = (int)t - 1;; base -= 32) {
+            const int p = base - (int)lane;
+            T         v = init;
+            unsigned  st = ST_INCL;
+            if (p >= 0) {
+                const uint64_t wd = wait_word(w0 - (int64_t)(t - (unsigned)p) * stride, epoch);
+                st                = word_status(wd, epoch);
+                v                 = st == ST_AGG_EMPTY ? empty : from_word(word_payload(wd));
+            }
+            const unsigned incl  = __ballot_sync(kFull, st == ST_INCL);
+            const unsigned first = incl ? (unsigned)__ffs((int)incl) - 1u : 31u;  // nearest inclusive predecessor
+            if (lane > first) v = empty;
+            // ordered fold: lane 0 is the latest tile, higher lanes are earlier
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const T o = shfl_down_T(v, d);
+                if (lane + d < 32u) v = comb(o, v);
+            }
+            const T round = shfl_T(v, 0);
+            acc           = comb(round, acc);
+            if (incl) break;
+        }
+        return acc;
+    }
+
+    // development aid (tools/phase_probe.py): with -DQB_TIMING thread 0 of every CTA stamps SM cycles at phase boundaries
+    // into the padding words of its tile's carry record
+#if defined(QB_TIMING) && !defined(QB_EMU)
+#define QB_STAMP(desc_ptr, word, slot, t0)                                                        \
+    do {                                                                                          \
+        if (threadIdx.x == 0) reinterpret_cast<unsigned*>((desc_ptr) + (word))[slot] = (unsigned)(clock64() - (t0)); \
+    } while (0)
+#define QB_T0() clock64()
+#else
+#define QB_STAMP(desc_ptr, word, slot, t0) do { } while (0)
+#define QB_T0() 0ll
+#endif
+
     __device__ __forceinline__ unsigned lanemask_lt(unsigned lane) { return (1u << lane) - 1u; }
     __device__ __forceinline__ unsigned lanemask_gt(unsigned lane) { return lane == 31 ? 0u : ~((2u << lane) - 1u); }
 

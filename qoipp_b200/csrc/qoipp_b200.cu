@@ -123,7 +123,10 @@ namespace
     template <typename Kern>
     cudaError_t allow_smem(Kern k, size_t bytes)
     {
-        return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        // the kernels hide look-back latency with resident CTAs: give shared memory the whole carve-out
+        return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
 
     cudaError_t set_attrs(qoipp_b200_ctx* c)
@@ -362,3 +365,11 @@ extern "C"
 }
 
 #include "decode_host.inl"
+
+#ifdef QB_TIMING
+extern "C" int32_t qoipp_b200_debug_carry(qoipp_b200_ctx* c, void** ptr, uint64_t* bytes)  // development aid only
+{
+    *ptr = c->carry.p, *bytes = c->carry.cap;
+    return 0;
+}
+#endif
