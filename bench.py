@@ -261,14 +261,19 @@ def main():
         decode()
         ev[3].record()
 
+    sampler = ClockSampler(local_rank)  # nvidia-smi needs ~100 ms to produce its first line: start before the warm-up
+    sampler.start()
     for _ in range(args.warmup):
         step([torch.cuda.Event(enable_timing=True) for _ in range(4)])
     torch.cuda.synchronize()
+    # keep the GPU under the same load until the sampler has delivered a few lines, then time
+    t_load = time.perf_counter()
+    while len(sampler.lines) < 3 and time.perf_counter() - t_load < 1.5:
+        step([torch.cuda.Event(enable_timing=True) for _ in range(4)])
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for ev in evs:

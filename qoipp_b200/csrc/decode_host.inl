@@ -72,15 +72,22 @@ extern "C"
         const unsigned tgt  = target ? target : desc->channels;
         const uint64_t need = (uint64_t)desc->width * desc->height * tgt;
         if (out_cap < need) return H::NotEnoughSpace;  // SURVEY hazard 3: the reference would write past the buffer
-        Guard g(c->device);
-        QB_CUDA(c->stage_in.reserve(qoi_size + 64));
-        QB_CUDA(c->stage_out.reserve(need + 64));
-        cudaStream_t s = c->own_stream;
-        QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_qoi, qoi_size, cudaMemcpyHostToDevice, s));
-        if (int32_t e = qoipp_b200_decode_dev(c, static_cast<uint8_t*>(c->stage_in.p), qoi_size, desc, (uint8_t)tgt, flip,
-                                              static_cast<uint8_t*>(c->stage_out.p), need, s))
-            return e;
-        QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, need, cudaMemcpyDeviceToHost, s));
+        Guard          g(c->device);
+        cudaStream_t   s     = c->own_stream;
+        const uint8_t* d_in  = mapped_host(h_qoi);  // page-locked buffers are used in place (zero-copy over PCIe)
+        uint8_t*       d_out = mapped_host(h_out);
+        if (!d_in) {
+            QB_CUDA(c->stage_in.reserve(qoi_size + 64));
+            QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_qoi, qoi_size, cudaMemcpyHostToDevice, s));
+            d_in = static_cast<uint8_t*>(c->stage_in.p);
+        }
+        const bool staged_out = d_out == nullptr;
+        if (staged_out) {
+            QB_CUDA(c->stage_out.reserve(need + 64));
+            d_out = static_cast<uint8_t*>(c->stage_out.p);
+        }
+        if (int32_t e = qoipp_b200_decode_dev(c, d_in, qoi_size, desc, (uint8_t)tgt, flip, d_out, need, s)) return e;
+        if (staged_out) QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, need, cudaMemcpyDeviceToHost, s));
         QB_CUDA(cudaStreamSynchronize(s));
         desc->channels = (uint8_t)tgt;  // :476 the returned Desc carries the target
         return 0;

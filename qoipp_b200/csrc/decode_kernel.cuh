@@ -609,20 +609,60 @@ namespace qb
         bool           bad      = false;
         for (unsigned k = tid; k < n_ops; k += kDecThreads) {
             const unsigned meta = sm.op_meta[k], kind = (meta >> 23) & 7u, val = sm.op_val[k];
-            const uint64_t pix = pix_base + (meta & 0x1FFFFu);
-            if (pix < N) {  // ops past the image are never executed by the reference
+            if (pix_base + (meta & 0x1FFFFu) < N) {  // ops past the image are never executed by the reference
                 if (kind == K_RGB) bad |= (val >> 24) != ((k ? sm.op_val[k - 1] : sm.in_state[64]) >> 24);  // simple.cpp:119-123
                 if (kind == K_INDEX) bad |= slot_of(val) != (meta >> 26);  // a never-written slot was read
             }
-            const unsigned np1 = (meta >> 17) & 63u;
-            if (np1 == 0) {
-                if (pix < N) store_pixel(out, pix, val, P);
-            } else {
-                for (unsigned j = 0; j <= np1 && pix + j < N; ++j) store_pixel(out, pix + j, val, P);  // OP_RUN, clamped (simple.cpp:158)
-            }
         }
         if (bad) sm.bad = 1;
-        __syncthreads();
+        if (P.flip) {  // bottom-up rows: pixels of a tile are not contiguous in the output, store them one by one
+            for (unsigned k = tid; k < n_ops; k += kDecThreads) {
+                const unsigned meta = sm.op_meta[k], val = sm.op_val[k];
+                const uint64_t pix  = pix_base + (meta & 0x1FFFFu);
+                const unsigned np1  = (meta >> 17) & 63u;
+                for (unsigned j = 0; j <= np1 && pix + j < N; ++j) store_pixel(out, pix + j, val, P);  // OP_RUN clamped (simple.cpp:158)
+            }
+            __syncthreads();
+        } else {
+            // pixels of the tile are one contiguous byte range of the output: expand runs into shared memory (the link
+            // array is dead by now) at the output's 16-byte phase, then leave as aligned uint4 stores
+            __syncthreads();  // all readers of sm.link are done
+            unsigned char* stg   = reinterpret_cast<unsigned char*>(sm.link);
+            const unsigned tgt   = P.target;
+            const unsigned pch   = tgt == 4 ? 4064u : 5440u;  // pixels per staging round: pch * tgt + 15 < sizeof(link)
+            const uint64_t avail = pix_base < N ? N - pix_base : 0;
+            const unsigned total = (unsigned)(avail < (uint64_t)sm.n_pix ? avail : (uint64_t)sm.n_pix);
+            for (unsigned c0 = 0; c0 < total; c0 += pch) {
+                const unsigned cn   = min(pch, total - c0);
+                uint8_t*       gdst = out + (pix_base + c0) * tgt;
+                const unsigned sh   = (unsigned)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+                for (unsigned k = tid; k < n_ops; k += kDecThreads) {
+                    const unsigned meta = sm.op_meta[k];
+                    const unsigned p0 = meta & 0x1FFFFu, p1 = p0 + ((meta >> 17) & 63u) + 1u;  // tile-relative pixel range
+                    if (p1 <= c0 || p0 >= c0 + cn) continue;
+                    const unsigned val = sm.op_val[k];
+                    const unsigned a = max(p0, c0) - c0, b = min(p1, c0 + cn) - c0;
+                    for (unsigned j = a; j < b; ++j) {
+                        unsigned char* d = stg + sh + j * tgt;
+                        if (tgt == 4 && (sh & 3u) == 0) *reinterpret_cast<unsigned*>(d) = val;
+                        else {
+                            d[0] = (unsigned char)val, d[1] = (unsigned char)(val >> 8), d[2] = (unsigned char)(val >> 16);
+                            if (tgt == 4) d[3] = (unsigned char)(val >> 24);
+                        }
+                    }
+                }
+                __syncthreads();
+                const unsigned nbytes = cn * tgt;
+                const unsigned head   = min(nbytes, (16u - sh) & 15u);
+                const unsigned nv     = (nbytes - head) >> 4;
+                if (tid < head) gdst[tid] = stg[sh + tid];
+                for (unsigned c = tid; c < nv; c += kDecThreads)
+                    reinterpret_cast<uint4*>(gdst + head)[c] = reinterpret_cast<const uint4*>(stg + sh + head)[c];
+                const unsigned done = head + (nv << 4);
+                if (tid < nbytes - done) gdst[done + tid] = stg[sh + done + tid];
+                __syncthreads();
+            }
+        }
         if (tid == 0 && sm.bad) atomicOr(&res->bad, 1u);
 
         QB_STAMP(desc, 71, 1, qb_t0);  // values + stores

@@ -182,6 +182,21 @@ namespace
         return 0;
     }
 
+    // A host pointer the device can dereference (page-locked memory under unified addressing: cudaHostAlloc /
+    // cudaHostRegister, e.g. torch pinned tensors), else nullptr.  Such buffers are read and written by the kernels
+    // directly over PCIe (zero-copy), so transfer and codec work overlap tile by tile with no staging copy.
+    template <class T>
+    T* mapped_host(T* p)
+    {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        if (a.type == cudaMemoryTypeHost && a.devicePointer) return static_cast<T*>(a.devicePointer);
+        return nullptr;
+    }
+
     unsigned pack_px(const uint8_t* p) { return p[0] | (unsigned)p[1] << 8 | (unsigned)p[2] << 16 | (unsigned)p[3] << 24; }
     void     unpack_px(unsigned v, uint8_t* p) { p[0] = (uint8_t)v, p[1] = (uint8_t)(v >> 8), p[2] = (uint8_t)(v >> 16), p[3] = (uint8_t)(v >> 24); }
 }  // namespace
@@ -288,14 +303,25 @@ extern "C"
         H::worst_size(*desc, &worst);
         Guard          g(c->device);
         const uint64_t cap = std::min(out_cap, worst);
-        QB_CUDA(c->stage_in.reserve(raw_size + 16));
-        QB_CUDA(c->stage_out.reserve(cap + 16));
-        cudaStream_t s = c->own_stream;
-        QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_raw, raw_size, cudaMemcpyHostToDevice, s));
-        if (int32_t e = qoipp_b200_encode_dev(c, static_cast<uint8_t*>(c->stage_in.p), desc, static_cast<uint8_t*>(c->stage_out.p), cap, s)) return e;
+        cudaStream_t   s   = c->own_stream;
+        const uint8_t* d_in  = mapped_host(h_raw);
+        uint8_t*       d_out = mapped_host(h_out);
+        if (!d_in) {
+            QB_CUDA(c->stage_in.reserve(raw_size + 16));
+            QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_raw, raw_size, cudaMemcpyHostToDevice, s));
+            d_in = static_cast<uint8_t*>(c->stage_in.p);
+        }
+        const bool staged_out = d_out == nullptr;
+        if (staged_out) {
+            QB_CUDA(c->stage_out.reserve(cap + 16));
+            d_out = static_cast<uint8_t*>(c->stage_out.p);
+        }
+        if (int32_t e = qoipp_b200_encode_dev(c, d_in, desc, d_out, cap, s)) return e;
         if (int32_t e = qoipp_b200_encode_status(c, s, written, complete)) return e;
-        if (*written) QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, *written, cudaMemcpyDeviceToHost, s));
-        QB_CUDA(cudaStreamSynchronize(s));
+        if (staged_out && *written) {
+            QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, *written, cudaMemcpyDeviceToHost, s));
+            QB_CUDA(cudaStreamSynchronize(s));
+        }
         return 0;
     }
 
