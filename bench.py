@@ -148,7 +148,7 @@ def cpu_reference(name: str, imgs, w, h, ch, budget_s: float = 20.0):
         "value": round(gbps_multi, 4), "unit": "GB/s", "cores": cores, "kind": kind,
         "sample": f"{name}: {w}x{rows}x{ch} encode_into+decode, thread-per-image on {cores} threads x {repsT} reps "
                   f"(single thread: {gbps_single:.4f} GB/s, {reps1} reps)",
-        "single_thread_value": round(gbps_single, 4),
+        "single_thread_value": round(gbps_single, 4), "sample_raw_bytes": int(raw.size),
     }
 
 
@@ -161,7 +161,8 @@ def run_reference_arm(args, rank):
     cb = cpu_reference(args.workload, imgs, w, h, ch, budget_s=min(60.0, 8.0 * max(1, args.steps)))
     line = {
         "impl": "reference", "metric": "raw_pixel_GBps_encode_decode", "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(2 * cb["sample_raw_bytes"] / (cb["value"] * 1e9) * 1e3, 5),
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "width": w, "height": h, "channels": ch, "images_per_rank": n},
         "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

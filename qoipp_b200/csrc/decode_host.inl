@@ -2,23 +2,34 @@
 namespace
 {
     // tile bookkeeping shared by the single-image and batch launches
+    constexpr size_t kCtrlBytes = 64;  // DecControl lives in front of the DecResult array
+    static_assert(sizeof(DecControl) <= kCtrlBytes, "control block");
+
     int32_t launch_decode(qoipp_b200_ctx* c, DecParams& P, cudaStream_t s)
     {
         QB_CUDA(set_attrs(c));
         QB_CUDA(c->tickets.reserve(64, true));
-        QB_CUDA(c->results.reserve(sizeof(DecResult) * P.n_images));
-        QB_CUDA(cudaMemsetAsync(c->results.p, 0, sizeof(DecResult) * P.n_images, s));
-        QB_CUDA(c->next_epoch((uint64_t)P.n_tiles * kDecDescWords * sizeof(uint64_t), s));
+        const size_t res_bytes = kCtrlBytes + sizeof(DecResult) * P.n_images;
+        QB_CUDA(c->results.reserve(res_bytes));
+        QB_CUDA(cudaMemsetAsync(c->results.p, 0, res_bytes, s));
+        QB_CUDA(c->fix.reserve((size_t)P.n_tiles * kFixWords * sizeof(uint32_t)));
+        // one epoch per possible round; the learned-alpha lists are tagged with the first one
+        QB_CUDA(c->next_epoch((uint64_t)P.n_tiles * kDecDescWords * sizeof(uint64_t), s, kDecRounds + 1));
         P.epoch   = c->epoch;
-        P.results = static_cast<DecResult*>(c->results.p);
+        P.round   = 0;
+        P.control = static_cast<DecControl*>(c->results.p);
+        P.results = reinterpret_cast<DecResult*>(static_cast<uint8_t*>(c->results.p) + kCtrlBytes);
         P.desc    = static_cast<uint64_t*>(c->carry.p);
+        P.fix     = static_cast<uint32_t*>(c->fix.p);
         P.ticket  = static_cast<uint32_t*>(c->tickets.p) + 1;
         decode_kernel<<<P.n_tiles, kDecThreads, sizeof(DecSmem), s>>>(P);
         QB_CUDA(cudaGetLastError());
-        SerialParams S{};
-        S.d = P, S.mode = 0;
-        decode_serial_kernel<<<P.n_images, 32, sizeof(SerialSmem), s>>>(S);  // exits at once unless the parallel path flagged the image
-        QB_CUDA(cudaGetLastError());
+        // Retry rounds and the sequential part are ONE cooperative launch enqueued unconditionally: it returns at once when
+        // round 0 verified every tile -- no host round trip, a few microseconds when nothing is to be done.
+        const unsigned grid = std::min<unsigned>(P.n_tiles, (unsigned)c->dec_coresident);
+        void*          args[] = { &P };
+        QB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_finish_kernel), dim3(grid), dim3(kDecThreads), args,
+                                            sizeof(DecSmem), s));
         return 0;
     }
 }
@@ -53,7 +64,7 @@ extern "C"
         Guard g(c->device);
         auto  s = static_cast<cudaStream_t>(stream);
         auto* h = static_cast<DecResult*>(c->h_result.p);
-        QB_CUDA(cudaMemcpyAsync(h, c->results.p, 16, cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaMemcpyAsync(h, static_cast<uint8_t*>(c->results.p) + kCtrlBytes, 16, cudaMemcpyDeviceToHost, s));
         QB_CUDA(cudaStreamSynchronize(s));
         if (path) *path = (int32_t)h->path;
         return 0;
@@ -149,7 +160,7 @@ extern "C"
         QB_CUDA(c->stage_in.reserve(in_size + 64));
         QB_CUDA(c->stage_out.reserve(cap + 64));
         QB_CUDA(c->state.reserve(sizeof(DecState)));
-        QB_CUDA(c->results.reserve(sizeof(DecResult)));
+        QB_CUDA(c->results.reserve(kCtrlBytes + sizeof(DecResult)));
         cudaStream_t s  = c->own_stream;
         auto*        hs = reinterpret_cast<DecState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
         hs->prev = pack_px(st->prev), hs->run = st->run;
@@ -160,12 +171,12 @@ extern "C"
         S.d.qoi = static_cast<uint8_t*>(c->stage_in.p), S.d.single[0] = 0, S.d.single[1] = in_size;
         S.d.out = static_cast<uint8_t*>(c->stage_out.p), S.d.out_stride = cap;  // mode 1: capacity in bytes
         S.d.target = ch, S.d.flip = 0, S.d.n_images = 1;
-        S.d.results = static_cast<DecResult*>(c->results.p);
+        S.d.results = reinterpret_cast<DecResult*>(static_cast<uint8_t*>(c->results.p) + kCtrlBytes);
         S.mode = 1, S.init = static_cast<DecState*>(c->state.p), S.in_size = in_size;
         decode_serial_kernel<<<1, 32, sizeof(SerialSmem), s>>>(S);
         QB_CUDA(cudaGetLastError());
         auto* hr = static_cast<DecResult*>(c->h_result.p);
-        QB_CUDA(cudaMemcpyAsync(hr, c->results.p, sizeof(DecResult), cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaMemcpyAsync(hr, static_cast<uint8_t*>(c->results.p) + kCtrlBytes, sizeof(DecResult), cudaMemcpyDeviceToHost, s));
         QB_CUDA(cudaStreamSynchronize(s));
         if (hr->written) {
             QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, hr->written, cudaMemcpyDeviceToHost, s));

@@ -36,13 +36,22 @@ namespace qb
         uint32_t table[64];
     };
 
+    constexpr int kDecRounds = 4;  // verification-driven retry rounds before the sequential kernel takes over
+
     struct DecResult {
-        uint32_t bad;   // parallel path: speculation refuted somewhere in this image
-        uint32_t path;  // 0 = parallel result stands, 1 = sequential kernel produced the pixels
+        uint32_t bad;   // round 0 refuted a speculation somewhere in this image
+        uint32_t path;  // retry rounds used; + 100 when the sequential kernel produced (part of) the image
         uint64_t pixels;
         uint64_t processed;  // resumable decode: input bytes consumed / output bytes written / carry-out
         uint64_t written;
+        uint32_t first_bad[kDecRounds + 1];  // per round: 0 = all verified, else 0xFFFFFFFF - first refuted tile
+        uint32_t pad[3];
         DecState state;
+    };
+
+    struct DecControl {  // zeroed with the results before every decode
+        uint32_t tickets[kDecRounds + 1];  // tile tickets of the retry rounds
+        uint32_t any_bad[kDecRounds + 1];  // some image needs round r + 1
     };
 
     struct DecParams {
@@ -54,11 +63,15 @@ namespace qb
         uint64_t        out_stride;
         uint64_t        n_pixels;
         uint32_t        width, height, target, flip;
-        uint32_t        n_images, n_tiles, epoch, pad;
+        uint32_t        n_images, n_tiles, epoch, round;  // epoch = first epoch of this decode, round r uses epoch + r
         DecResult*      results;
+        DecControl*     control;
         uint64_t*       desc;
+        uint32_t*       fix;  // [n_tiles][kFixWords]: alpha learned at OP_RGB ops by earlier rounds
         uint32_t*       ticket;
     };
+
+    constexpr int kFixWords = 32, kFixMax = kFixWords - 1;  // word 0: count | decode tag << 8; entries: pos | alpha << 16
 
     constexpr int kDecThreads = 256, kDecWarps = 8, kDecSB = 8, kDecTB = kDecThreads * kDecSB;
     constexpr int kDecDescWords = 72;
@@ -178,7 +191,8 @@ namespace qb
         Seg            wseg[kDecWarps];
         Map            wmap[kDecWarps];
         uint64_t       pix_base;
-        unsigned       ticket, entry, slot_in, alpha_in, n_ops, n_pix, bad, changed;
+        unsigned       fixe[kFixMax];
+        unsigned       ticket, entry, slot_in, alpha_in, n_ops, n_pix, bad, changed, fixn, fixn0, fix_dirty;
     };
 
     // op walk of one thread's sub-chunk: f(pos, tag) for every op whose tag lies in [8*tid, 8*tid + 8) and below `limit`
@@ -291,30 +305,42 @@ namespace qb
         stream = P.qoi + o0, size = __ldg(P.offsets + lo + 1) - o0;
     }
 
-    __global__ void __launch_bounds__(kDecThreads, 5) decode_kernel(const DecParams P)
+    // learned alpha for the OP_RGB at byte position p of this tile (earlier rounds), if any
+    __device__ __forceinline__ bool fix_lookup(const DecSmem& sm, unsigned p, unsigned& alpha)
     {
-        DecSmem&       sm  = *reinterpret_cast<DecSmem*>(QB_DYN_SMEM);
+        for (unsigned j = 0; j < sm.fixn0; ++j)
+            if ((sm.fixe[j] & 0xFFFFu) == p) { alpha = (sm.fixe[j] >> 16) & 255u; return true; }
+        return false;
+    }
+
+    // one tile (global ticket sm.ticket) of round `round`; all threads of the CTA
+    __device__ __forceinline__ void decode_tile(const DecParams& P, DecSmem& sm, unsigned round, unsigned img, unsigned t, unsigned ntiles,
+                                                const uint8_t* stream, uint64_t size, unsigned fresh_from)
+    {
         const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
         [[maybe_unused]] const long long qb_t0 = QB_T0();
-
-        if (tid == 0) {
-            sm.ticket  = atomicInc(P.ticket, P.n_tiles - 1u);
-            sm.bad     = 0;
-            sm.changed = 0;
-        }
-        __syncthreads();
-        unsigned       img, t, ntiles;
-        const uint8_t* stream;
-        uint64_t       size;
-        locate_image(P, sm.ticket, img, t, ntiles, stream, size);
         const uint64_t body_len = size - kHeader;  // every byte after the header is chunk data (simple.cpp:110-113)
         const uint64_t tile_b0  = (uint64_t)t * kDecTB;
         const unsigned limit    = (unsigned)(body_len - tile_b0 < (uint64_t)kDecTB ? body_len - tile_b0 : (uint64_t)kDecTB);
         uint64_t*      desc     = P.desc + (uint64_t)sm.ticket * kDecDescWords;
-        const unsigned epoch    = P.epoch;
+        const unsigned epoch    = P.epoch + round;
+        const Epochs   ep{ epoch, P.epoch, fresh_from };
         uint8_t*       out      = P.out + (uint64_t)img * P.out_stride;
         const uint64_t N        = P.n_pixels;
         DecResult*     res      = P.results + img;
+        uint32_t*      fix      = P.fix + (uint64_t)sm.ticket * kFixWords;
+        auto word_of = [&](unsigned p, int which) { return desc - (int64_t)(t - p) * kDecDescWords + which; };
+
+        // alpha values learned by earlier rounds for OP_RGB ops of this tile
+        if (tid < kFixWords) {
+            unsigned n = 0;
+            if (round > 0) {
+                const unsigned h = fix[0];
+                if ((h >> 8) == (P.epoch & 0xFFFFFFu)) n = min(h & 255u, (unsigned)kFixMax);
+                if (tid >= 1 && tid <= n) sm.fixe[tid - 1] = fix[tid];
+            }
+            if (tid == 0) sm.fixn = n, sm.fixn0 = n, sm.fix_dirty = 0, sm.bad = 0;
+        }
 
         // ---- stage the tile: 16-byte aligned chunks land at the same misalignment in shared memory
         const uint8_t* src   = stream + kHeader + tile_b0;
@@ -350,8 +376,13 @@ namespace qb
         if (w == 0) {  // 32 predecessors per look-back round; an inclusive word is the constant map "exit offset"
             if (lane == 0 && t > 0) st_word(desc + kDwParse, pack_word(map_pack(tile_map), ST_AGG, epoch));
             const Map in = warp_lookback<Map>(
-                desc + kDwParse, t, kDecDescWords, epoch, map_const(0), map_identity(),
-                [](uint64_t pl) { return map_unpack((unsigned)pl); }, [](const Map& a, const Map& b) { return map_compose(a, b); });
+                t, map_const(0), map_identity(),
+                [&](unsigned p, unsigned& st) {
+                    const uint64_t wd = wait_word(word_of(p, kDwParse), ep, p);
+                    st                = raw_status(wd);
+                    return map_unpack((unsigned)word_payload(wd));
+                },
+                [](const Map& a, const Map& b) { return map_compose(a, b); });
             const unsigned entry = in.lo & 7u;  // `in` is constant: every chain ended in an inclusive word
             if (lane == 0) {
                 st_word(desc + kDwParse, pack_word(map_pack(map_const(map_at(tile_map, entry))), ST_INCL, epoch));
@@ -374,8 +405,9 @@ namespace qb
                 sm.link[p] = (uint64_t)(o.kind | (o.npix - 1u) << 3 | o.lin << 9) << 32 | o.data;
                 cnt += o.npix | 1u << 20;
                 switch (o.kind) {
-                case K_RGB:  // slot needs the inherited alpha: resolved here if an OP_RGBA came earlier in this sub-chunk
+                case K_RGB:  // slot needs the inherited alpha: known if an OP_RGBA (or a learned alpha) came earlier here
                     rootpos = p, delta = 0;
+                    if (sm.fixn0 && fix_lookup(sm, p, alpha)) flags |= kFlRgba;  // an earlier round learned the alpha at this op
                     if (flags & kFlRgba) c = o.lin + 11u * alpha, flags = kFlRoot | kFlRgba;
                     else c = o.lin, flags = kFlRoot | kFlUses;
                     break;
@@ -396,7 +428,12 @@ namespace qb
             const unsigned npix = tot.cnt & 0xFFFFFu;
             if (lane == 0 && t > 0) st_word(desc + kDwPix, pack_word(npix, ST_AGG, epoch));
             const uint64_t base = warp_lookback<uint64_t>(
-                desc + kDwPix, t, kDecDescWords, epoch, (uint64_t)0, (uint64_t)0, [](uint64_t pl) { return pl; },
+                t, (uint64_t)0, (uint64_t)0,
+                [&](unsigned p, unsigned& st) {
+                    const uint64_t wd = wait_word(word_of(p, kDwPix), ep, p);
+                    st                = raw_status(wd);
+                    return word_payload(wd);
+                },
                 [](uint64_t a, uint64_t b) { return a + b; });
             if (lane == 0) {
                 const uint64_t total = base + npix;
@@ -415,8 +452,19 @@ namespace qb
             };
             const Seg start = Seg{ 0u, 255u << 24, 53u << 16 | kFlRoot | kFlRgba };  // {0,0,0,255}: slot 53 (simple.cpp:108)
             if (lane == 0 && t > 0) st_word(desc + kDwSlot, pack_word(pack(tot), ST_AGG, epoch));
-            const Seg acc = warp_lookback<Seg>(desc + kDwSlot, t, kDecDescWords, epoch, start, seg_identity(), unpack,
-                                               [](const Seg& a, const Seg& b) { return combine(a, b); });
+            const Seg acc = warp_lookback<Seg>(
+                t, start, seg_identity(),
+                [&](unsigned p, unsigned& st) {
+                    if (p < ep.fresh_from) {  // a tile finished by an earlier round: take slot and alpha of its actual last pixel
+                        const unsigned v = (unsigned)word_payload(wait_word(word_of(p, kDwState + 64), ep, p));
+                        st               = ST_INCL;
+                        return Seg{ 0u, v & 0xFF000000u, slot_of(v) << 16 | kFlRoot | kFlRgba };
+                    }
+                    const uint64_t wd = wait_word(word_of(p, kDwSlot), ep, p);
+                    st                = raw_status(wd);
+                    return unpack(word_payload(wd));
+                },
+                [](const Seg& a, const Seg& b) { return combine(a, b); });
             if (lane == 0) {
                 sm.slot_in  = (acc.fl >> 16) & 63u;  // concrete: the chain ended in an inclusive word
                 sm.alpha_in = acc.da >> 24;
@@ -444,6 +492,7 @@ namespace qb
                 const unsigned kind = meta & 7u, npix1 = (meta >> 3) & 63u, lin = (meta >> 9) & 63u;
                 switch (kind) {
                 case K_RGB: {
+                    if (sm.fixn0) fix_lookup(sm, p, alpha);
                     const unsigned lit = data | alpha << 24;  // speculated alpha, verified below
                     slot = slot_of(lit), root = p, delta = 0;
                     sm.link[p] = (uint64_t)kPtrConst << 32 | lit;
@@ -573,9 +622,9 @@ namespace qb
                     v = add4((e == 64 || e == 53) ? kStartPixel : 0u, acc);
                     break;
                 }
-                const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kDecDescWords + kDwState + e, epoch);
+                const uint64_t wd = wait_word(word_of((unsigned)p, kDwState + (int)e), ep, (unsigned)p);
                 const uint64_t pl = word_payload(wd);
-                if (word_status(wd, epoch) == ST_INCL) { v = add4((unsigned)pl, acc); break; }
+                if (raw_status(wd) == ST_INCL) { v = add4((unsigned)pl, acc); break; }
                 acc = add4(acc, (unsigned)pl);
                 const unsigned c = (unsigned)(pl >> 32);
                 if (c == 65u) { v = acc; break; }
@@ -610,8 +659,21 @@ namespace qb
         for (unsigned k = tid; k < n_ops; k += kDecThreads) {
             const unsigned meta = sm.op_meta[k], kind = (meta >> 23) & 7u, val = sm.op_val[k];
             if (pix_base + (meta & 0x1FFFFu) < N) {  // ops past the image are never executed by the reference
-                if (kind == K_RGB) bad |= (val >> 24) != ((k ? sm.op_val[k - 1] : sm.in_state[64]) >> 24);  // simple.cpp:119-123
-                if (kind == K_INDEX) bad |= slot_of(val) != (meta >> 26);  // a never-written slot was read
+                if (kind == K_RGB) {  // simple.cpp:119-123: the alpha is inherited from the previous pixel
+                    const unsigned actual = (k ? sm.op_val[k - 1] : sm.in_state[64]) >> 24;
+                    if ((val >> 24) != actual) {
+                        bad = true;
+                        // remember the alpha seen here for the next round (exact if everything before this op was exact)
+                        const unsigned p = sm.op_pos[k], e = p | actual << 16;
+                        unsigned       j = 0;
+                        for (; j < sm.fixn0; ++j)
+                            if ((sm.fixe[j] & 0xFFFFu) == p) break;
+                        if (j == sm.fixn0) j = atomicAdd(&sm.fixn, 1u);
+                        if (j < (unsigned)kFixMax) sm.fixe[j] = e;
+                        sm.fix_dirty = 1;
+                    }
+                }
+                if (kind == K_INDEX) bad |= slot_of(val) != (meta >> 26);  // a never-written (or mis-predicted) slot was read
             }
         }
         if (bad) sm.bad = 1;
@@ -663,7 +725,18 @@ namespace qb
                 __syncthreads();
             }
         }
-        if (tid == 0 && sm.bad) atomicOr(&res->bad, 1u);
+        // a refuted tile makes the image eligible for the next round, from the first such tile on
+        if (sm.bad) {
+            if (tid == 0) {
+                if (round == 0) atomicOr(&res->bad, 1u);
+                atomicMax(&res->first_bad[round], 0xFFFFFFFFu - t);
+                P.control->any_bad[round] = 1;
+            }
+            if (sm.fix_dirty && tid < kFixWords) {
+                const unsigned n = min(sm.fixn, (unsigned)kFixMax);
+                fix[tid] = tid == 0 ? (n | (P.epoch & 0xFFFFFFu) << 8) : (tid <= n ? sm.fixe[tid - 1] : 0u);
+            }
+        }
 
         QB_STAMP(desc, 71, 1, qb_t0);  // values + stores
         // ---- the stream ended before the image: the zero padding decodes as INDEX 0 forever (simple.cpp:106,132-135)
@@ -672,10 +745,26 @@ namespace qb
             const unsigned fill = sm.fn_add[0];
             if (tid == 0) {
                 res->pixels = have < N ? have : N;
-                if (have < N && slot_of(fill) != 0) atomicOr(&res->bad, 1u);
+                if (have < N && slot_of(fill) != 0) {  // cannot happen while the table invariant holds; be safe
+                    atomicMax(&res->first_bad[round], 0xFFFFFFFFu - t);
+                    P.control->any_bad[round] = 1;
+                }
             }
             for (uint64_t pix = have + tid; pix < N; pix += kDecThreads) store_pixel(out, pix, fill, P);
         }
+    }
+
+    // round 0: one tile per CTA
+    __global__ void __launch_bounds__(kDecThreads, 5) decode_kernel(const DecParams P)
+    {
+        DecSmem& sm = *reinterpret_cast<DecSmem*>(QB_DYN_SMEM);
+        if (threadIdx.x == 0) sm.ticket = atomicInc(P.ticket, P.n_tiles - 1u);
+        __syncthreads();
+        unsigned       img, t, ntiles;
+        const uint8_t* stream;
+        uint64_t       size;
+        locate_image(P, sm.ticket, img, t, ntiles, stream, size);
+        decode_tile(P, sm, 0u, img, t, ntiles, stream, size, 0u);
     }
 
     // =====================================================================================================
@@ -698,19 +787,29 @@ namespace qb
         unsigned      ctl[8];
     };
 
-    __global__ void __launch_bounds__(32) decode_serial_kernel(const SerialParams S)
+    // one warp; `img` selects the image (mode 0) -- called by decode_finish_kernel and decode_serial_kernel
+    __device__ __forceinline__ void decode_serial_body(const SerialParams& S, SerialSmem& sm, unsigned img)
     {
-        SerialSmem&           sm   = *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM);
         const DecParams&      P    = S.d;
-        const unsigned        lane = threadIdx.x;
-        const unsigned        img  = blockIdx.x;
+        const unsigned        lane = threadIdx.x & 31u;
         DecResult*            res  = P.results + img;
-        if (S.mode == 0 && res->bad == 0) return;
+        unsigned restart = 0;  // mode 0: first tile to decode again (the tiles before it verified in some round)
+        if (S.mode == 0) {
+            unsigned rounds = 0;
+            for (int r = 0; r < kDecRounds; ++r)
+                if (res->first_bad[r]) rounds = r + 1;
+            const unsigned fb = res->first_bad[kDecRounds];
+            __syncwarp();
+            if (lane == 0) res->path = rounds + (fb ? 100u : 0u);
+            if (fb == 0) return;
+            restart = 0xFFFFFFFFu - fb;
+        }
 
         const uint8_t* stream;
         uint64_t       size;
+        unsigned       first_tile = 0;
         if (P.tile_first == nullptr) stream = P.qoi + P.single[0], size = P.single[1] - P.single[0];
-        else stream = P.qoi + P.offsets[img], size = P.offsets[img + 1] - P.offsets[img];
+        else stream = P.qoi + P.offsets[img], size = P.offsets[img + 1] - P.offsets[img], first_tile = P.tile_first[img];
         uint8_t*       out   = P.out + (uint64_t)img * (S.mode == 0 ? P.out_stride : 0);
         const uint8_t* body  = S.mode == 0 ? stream + kHeader : stream;
         const uint64_t blen  = S.mode == 0 ? size - kHeader : S.in_size;
@@ -719,15 +818,22 @@ namespace qb
         sm.table[lane] = 0, sm.table[lane + 32] = 0;
         __syncwarp();
         unsigned prev = kStartPixel, run = 0;
+        uint64_t pos = 0, px = 0;  // consumed input bytes, produced pixels
         if (S.mode == 1) {
             prev = S.init->prev, run = S.init->run;
             sm.table[lane] = S.init->table[lane], sm.table[lane + 32] = S.init->table[lane + 32];
+        } else if (restart > 0) {
+            // resume behind the last verified tile: its inclusive carry words are the decoder state at that point
+            const uint64_t* d = P.desc + (uint64_t)(first_tile + restart - 1) * kDecDescWords;
+            pos               = (uint64_t)restart * kDecTB + (word_payload(d[kDwParse]) & 7u);
+            px                = word_payload(d[kDwPix]);
+            prev              = (unsigned)word_payload(d[kDwState + 64]);
+            sm.table[lane] = (unsigned)word_payload(d[kDwState + lane]), sm.table[lane + 32] = (unsigned)word_payload(d[kDwState + 32 + lane]);
         } else if (lane == 0) {
             sm.table[53] = kStartPixel;  // simple.cpp:108
         }
         __syncwarp();
 
-        uint64_t pos = 0, px = 0;  // consumed input bytes, produced pixels
         bool     stop = false;
         while (!stop && px < room) {
             // stage kSerIn bytes from `pos` (zero padded in mode 0)
@@ -770,7 +876,7 @@ namespace qb
             if (ip == 0 && op == 0) break;
         }
         if (S.mode == 0) {
-            if (lane == 0) res->path = 1, res->pixels = px;
+            if (lane == 0) res->pixels = px;
             return;
         }
         // mode 1 carry-out.  A run that is still pending when the input of mode 0 ends is dropped by the clamp
@@ -783,10 +889,53 @@ namespace qb
         }
     }
 
+    // resumable decode (mode 1): one warp
+    __global__ void __launch_bounds__(32) decode_serial_kernel(const SerialParams S)
+    {
+        decode_serial_body(S, *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM), 0u);
+    }
+
+    // Everything after round 0, in ONE cooperative launch of co-resident persistent CTAs (so that an image that
+    // verified costs a single empty launch): rounds 1..kDecRounds re-decode, per image, the tiles from the first refuted
+    // one on with the alphas learned by the round before (grid-wide barrier between rounds); what still fails after the
+    // last round is decoded by the sequential loop, one warp per image, resuming behind the last verified tile.
+    __global__ void __launch_bounds__(kDecThreads, 5) decode_finish_kernel(const DecParams P)
+    {
+        DecSmem& sm = *reinterpret_cast<DecSmem*>(QB_DYN_SMEM);
+        for (unsigned round = 1; round <= (unsigned)kDecRounds; ++round) {
+            if (P.control->any_bad[round - 1] == 0) break;  // same value in every CTA: final since the last barrier
+            for (;;) {
+                __syncthreads();  // the previous tile's shared memory is no longer in use
+                if (threadIdx.x == 0) sm.ticket = atomicAdd(&P.control->tickets[round], 1u);
+                __syncthreads();
+                if (sm.ticket >= P.n_tiles) break;
+                unsigned       img, t, ntiles;
+                const uint8_t* stream;
+                uint64_t       size;
+                locate_image(P, sm.ticket, img, t, ntiles, stream, size);
+                const unsigned fb = P.results[img].first_bad[round - 1];
+                if (fb == 0 || t < 0xFFFFFFFFu - fb) continue;  // image verified, or a tile before the first refuted one: final
+                decode_tile(P, sm, round, img, t, ntiles, stream, size, 0xFFFFFFFFu - fb);
+            }
+            QB_GRID_SYNC();
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            SerialParams S{};
+            S.d = P, S.mode = 0;
+            for (unsigned img = blockIdx.x; img < P.n_images; img += gridDim.x)
+                decode_serial_body(S, *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM), img);
+        }
+    }
+
 #ifndef QB_EMU
     inline cudaError_t dec_set_attrs()
     {
         cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecSmem));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }

@@ -287,8 +287,13 @@ namespace qb
             }
             // payload = last differing pixel index + bias (never 0); the later tile wins when it has one
             const uint64_t lp = warp_lookback<uint64_t>(
-                desc + kWordLne, t, kEncDescWords, epoch, (uint64_t)(kLneBias - 1 - run_in), (uint64_t)0,
-                [](uint64_t pl) { return pl; }, [](uint64_t a, uint64_t b) { return b ? b : a; });
+                t, (uint64_t)(kLneBias - 1 - run_in), (uint64_t)0,
+                [&](unsigned p, unsigned& st) {
+                    const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kEncDescWords + kWordLne, epoch);
+                    st                = word_status(wd, epoch);
+                    return word_payload(wd);
+                },
+                [](uint64_t a, uint64_t b) { return b ? b : a; });
             if (lane == 0) {
                 if (tl < 0) st_word(desc + kWordLne, pack_word(lp, ST_INCL, epoch));
                 sm.lne_payload = lp;
@@ -368,8 +373,13 @@ namespace qb
             for (int ww = 0; ww < kEncWarps; ++ww) acc += sm.wbytes[ww];
             if (lane == 0 && t > 0) st_word(desc + kWordBytes, pack_word(acc, ST_AGG, epoch));
             const uint64_t off = warp_lookback<uint64_t>(
-                desc + kWordBytes, t, kEncDescWords, epoch, (uint64_t)(stream ? 0u : kHeader), (uint64_t)0,
-                [](uint64_t pl) { return pl; }, [](uint64_t a, uint64_t b) { return a + b; });
+                t, (uint64_t)(stream ? 0u : kHeader), (uint64_t)0,
+                [&](unsigned p, unsigned& st) {
+                    const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kEncDescWords + kWordBytes, epoch);
+                    st                = word_status(wd, epoch);
+                    return word_payload(wd);
+                },
+                [](uint64_t a, uint64_t b) { return a + b; });
             if (lane == 0) {
                 st_word(desc + kWordBytes, pack_word(off + acc, ST_INCL, epoch));
                 sm.pre = pre, sm.tile_total = acc, sm.tile_off = off;

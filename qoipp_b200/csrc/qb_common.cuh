@@ -11,7 +11,9 @@
 #include <stdint.h>
 
 #ifndef QB_EMU
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#define QB_GRID_SYNC() cooperative_groups::this_grid().sync()
 #define QB_SPIN_YIELD() __nanosleep(32)
 #define QB_DYN_SMEM qb_dyn_smem
 extern __shared__ __align__(128) unsigned char qb_dyn_smem[];
@@ -103,25 +105,47 @@ namespace qb
         return r;
     }
 
+    // ---- which launch epochs a reader accepts for the words of tile p.
+    // A decode is up to kRounds + 1 launches with consecutive epochs base, base+1, ...: in round r the tiles from
+    // `fresh_from` on are recomputed and must be read at epoch `cur`; earlier tiles are final and carry any epoch of this
+    // decode.  Encode (and round 0) use fresh_from = 0, i.e. an exact match.
+    struct Epochs {
+        unsigned cur, base, fresh_from;
+        __device__ __forceinline__ bool valid(uint64_t w, unsigned p) const
+        {
+            const unsigned e = ((unsigned)(w >> 34)) & kEpochMask;
+            if (((unsigned)(w >> 32) & 3u) == ST_NONE) return false;
+            return p >= fresh_from ? e == (cur & kEpochMask) : ((e - base) & kEpochMask) < ((cur - base) & kEpochMask);
+        }
+    };
+    __device__ __forceinline__ uint64_t wait_word(const uint64_t* ptr, const Epochs& ep, unsigned p)
+    {
+        uint64_t w = ld_word(ptr);
+        while (!ep.valid(w, p)) {
+            QB_SPIN_YIELD();
+            w = ld_word(ptr);
+        }
+        return w;
+    }
+    __device__ __forceinline__ unsigned raw_status(uint64_t w) { return (unsigned)(w >> 32) & 3u; }
+
     // ---- warp-cooperative decoupled look-back (all 32 lanes of ONE warp call this together)
-    // Lane l inspects predecessor base - l of tile t; words are `stride` uint64 apart, `w0` is tile t's own word.
-    // Status ST_AGG / ST_AGG_EMPTY carries the tile's own aggregate, ST_INCL the inclusive prefix; the virtual tile -1
-    // is inclusive with payload `init`.  Returns, in every lane, pred(t-1) (+) ... folded onto nothing, i.e. the exclusive
-    // prefix of tile t.  `comb(earlier, later)` must be associative; `empty` is its identity (used for ST_AGG_EMPTY too).
-    template <class T, class FromWord, class Comb>
-    __device__ __forceinline__ T warp_lookback(const uint64_t* w0, unsigned t, unsigned stride, unsigned epoch, T init, T empty,
-                                               FromWord from_word, Comb comb)
+    // Lane l inspects predecessor base - l of tile t.  `fetch(p, st)` waits for tile p's word and returns its value with
+    // st = ST_AGG / ST_AGG_EMPTY (the tile's own aggregate; EMPTY values are ignored) or ST_INCL (inclusive prefix).
+    // The virtual tile -1 is inclusive with value `init`.  Returns, in every lane, the exclusive prefix of tile t.
+    // `comb(earlier, later)` must be associative with identity `empty`.
+    template <class T, class Fetch, class Comb>
+    __device__ __forceinline__ T warp_lookback(unsigned t, T init, T empty, Fetch fetch, Comb comb)
     {
         const unsigned lane = threadIdx.x & 31u;
         T              acc  = empty;
         for (int base = (int)t - 1;; base -= 32) {
-            const int p = base - (int)lane;
-            T         v = init;
+            const int p  = base - (int)lane;
+            T         v  = init;
             unsigned  st = ST_INCL;
             if (p >= 0) {
-                const uint64_t wd = wait_word(w0 - (int64_t)(t - (unsigned)p) * stride, epoch);
-                st                = word_status(wd, epoch);
-                v                 = st == ST_AGG_EMPTY ? empty : from_word(word_payload(wd));
+                v = fetch((unsigned)p, st);
+                if (st == ST_AGG_EMPTY) v = empty;
             }
             const unsigned incl  = __ballot_sync(kFull, st == ST_INCL);
             const unsigned first = incl ? (unsigned)__ffs((int)incl) - 1u : 31u;  // nearest inclusive predecessor

@@ -90,16 +90,19 @@ struct qoipp_b200_ctx {
     DevBuf   tickets;     // [0] encode ticket, [1..] decode tickets
     DevBuf   results;     // EncResult[n_images] / DecResult
     DevBuf   state;       // EncState / DecState carry-in for the resumable calls
-    DevBuf   aux;         // decode: per-tile entry table etc.
+    DevBuf   aux;         // decode: per-image offsets and first-tile ids of a batch
+    DevBuf   fix;         // decode: per-tile lists of alphas learned by the retry rounds
     DevBuf   stage_in, stage_out;  // device staging of the host-pointer calls
     PinnedBuf h_result;   // pinned landing zone for result structs
     PinnedBuf h_pin_in, h_pin_out;
     cudaStream_t own_stream = nullptr;
     bool     enc_trivial = false;  // last encode needed no launch (capacity below the header)
     bool     attrs_set   = false;
+    int      dec_coresident = 148;  // CTAs of decode_finish_kernel that fit on the device at once
 
-    // next epoch; the carry buffer is cleared when the 20-bit counter wraps or the buffer was (re)allocated
-    cudaError_t next_epoch(size_t carry_bytes, cudaStream_t s)
+    // reserves `count` consecutive epochs and returns with `epoch` = the first; the carry buffer (and the tagged
+    // learned-alpha lists) are cleared when the 20-bit counter would wrap or the buffer was (re)allocated
+    cudaError_t next_epoch(size_t carry_bytes, cudaStream_t s, unsigned count = 1)
     {
         const bool grew = carry_bytes > carry.cap;
         if (grew) {
@@ -108,14 +111,17 @@ struct qoipp_b200_ctx {
             e = carry.reserve(carry_bytes, true);
             if (e != cudaSuccess) return e;
         }
-        epoch = (epoch + 1) & kEpochMask;
-        if (epoch == 0) {
+        epoch += span;  // skip the epochs the previous call reserved
+        span = count;
+        if (epoch == 0 || epoch + count > kEpochMask) {
             cudaError_t e = cudaMemsetAsync(carry.p, 0, carry.cap, s);
+            if (e == cudaSuccess && fix.p) e = cudaMemsetAsync(fix.p, 0, fix.cap, s);
             if (e != cudaSuccess) return e;
             epoch = 1;
         }
         return cudaSuccess;
     }
+    unsigned span = 1;
 };
 
 namespace
@@ -136,6 +142,9 @@ namespace
         if ((e = allow_smem(encode_kernel<3, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
         if ((e = allow_smem(encode_kernel<4, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
         if ((e = dec_set_attrs()) != cudaSuccess) return e;
+        int per_sm = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_finish_kernel, kDecThreads, sizeof(DecSmem))) != cudaSuccess) return e;
+        c->dec_coresident = std::max(1, per_sm) * c->sm_count;
         c->attrs_set = true;
         return cudaSuccess;
     }
@@ -253,7 +262,7 @@ extern "C"
         if (!c) return 0;
         Guard g(c->device);
         cudaDeviceSynchronize();
-        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release();
+        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release();
         c->stage_in.release(), c->stage_out.release();
         c->h_result.release(), c->h_pin_in.release(), c->h_pin_out.release();
         if (c->own_stream) cudaStreamDestroy(c->own_stream);

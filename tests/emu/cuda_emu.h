@@ -45,7 +45,7 @@ namespace emu
 {
     constexpr int kStack = 96 * 1024;
 
-    enum class Wait : uint8_t { None, Warp, Block, Spin };
+    enum class Wait : uint8_t { None, Warp, Block, Spin, Grid };
 
     struct Cta;
     struct Fiber {
@@ -83,6 +83,8 @@ namespace emu
         std::mt19937_64        rng{ 12345 };
         bool                   random_order = false;
         uint64_t               switches = 0;
+        uint64_t               grid_gen = 0;
+        unsigned               grid_arrived = 0, grid_expected = 0;
     };
     inline Ctx& ctx() { static Ctx c; return c; }
 
@@ -146,6 +148,7 @@ emu_switch:
         c.random_order = seed != 0;
         c.rng.seed(seed ? seed : 1);
         const unsigned nthreads = block.x, nwarps = (nthreads + 31) / 32, total = grid.x;
+        c.grid_arrived = 0; c.grid_expected = total * nthreads;
         static std::vector<Cta*> pool;  // fiber stacks are reused across launches
         std::vector<Cta*> live;
         unsigned next = 0;
@@ -178,6 +181,7 @@ emu_switch:
                     if (f.done) continue;
                     if (f.wait == Wait::Warp && k->warps[f.tid / 32].gen == f.wait_gen) continue;
                     if (f.wait == Wait::Block && k->bar_gen == f.wait_gen) continue;
+                    if (f.wait == Wait::Grid && c.grid_gen == f.wait_gen) continue;
                     bool was_spin = f.wait == Wait::Spin;
                     f.wait = Wait::None;
                     c.cur = &f;
@@ -275,6 +279,20 @@ emu_switch:
         return 0;
     }
 
+    // cooperative-groups grid barrier: every thread of every CTA of the launch (all CTAs must be resident)
+    inline void grid_barrier()
+    {
+        Ctx&   c = ctx();
+        Fiber& f = *c.cur;
+        if (++c.grid_arrived == c.grid_expected) {
+            c.grid_arrived = 0;
+            ++c.grid_gen;
+        } else {
+            f.wait = Wait::Grid; f.wait_gen = c.grid_gen;
+            yield_to_sched();
+        }
+    }
+
     inline void spin_yield()
     {
         Fiber& f = *ctx().cur;
@@ -291,6 +309,7 @@ emu_switch:
 #define warpSize 32
 #define QB_DYN_SMEM (emu::ctx().cur->cta->smem.data() + ((128 - ((uintptr_t)emu::ctx().cur->cta->smem.data() & 127)) & 127))
 #define QB_SPIN_YIELD() emu::spin_yield()
+#define QB_GRID_SYNC() emu::grid_barrier()
 
 // ---------------------------------------------------------------- intrinsics
 static inline void     __syncthreads() { emu::block_barrier(0); }

@@ -107,18 +107,24 @@ extern "C"
         P.width = w; P.height = h; P.target = target; P.flip = flip;
         P.n_images = n_images; P.n_tiles = (uint32_t)tiles; P.epoch = 3;
         std::vector<uint64_t>  desc((size_t)tiles * kDecDescWords, 0);
+        std::vector<uint32_t>  fix((size_t)tiles * kFixWords, 0xDEADBEEFu);
         std::vector<DecResult> res(n_images);
+        DecControl             ctl;
         memset(res.data(), 0, sizeof(DecResult) * n_images);
+        memset(&ctl, 0, sizeof ctl);
         uint32_t ticket = 0;
-        P.desc = desc.data(); P.results = res.data(); P.ticket = &ticket;
-        if (!force_serial)
+        P.desc = desc.data(); P.results = res.data(); P.control = &ctl; P.fix = fix.data(); P.ticket = &ticket;
+        P.epoch = 5; P.round = 0;
+        if (!force_serial) {
             emu::launch(dim3(P.n_tiles), dim3(kDecThreads), sizeof(DecSmem) + 128, [=] { decode_kernel(P); }, resident, seed);
-        else
-            for (auto& r : res) r.bad = 1;
-        if (ticket != 0) return -1;
-        SerialParams S{};
-        S.d = P; S.mode = 0;
-        emu::launch(dim3(n_images), dim3(32), sizeof(SerialSmem) + 128, [=] { decode_serial_kernel(S); }, resident, seed);
+            if (ticket != 0) return -1;
+        } else {
+            for (auto& r : res) r.first_bad[kDecRounds] = 0xFFFFFFFFu;  // "tile 0 refuted in the last round"
+        }
+        {   // cooperative launch: every CTA resident
+            const unsigned g = std::min<unsigned>(P.n_tiles, 3u);
+            emu::launch(dim3(g), dim3(kDecThreads), sizeof(DecSmem) + 128, [=] { decode_finish_kernel(P); }, (int)g, seed + 1);
+        }
         for (uint32_t k = 0; k < n_images; ++k) out_path[k] = (int)res[k].path;
         return 0;
     }

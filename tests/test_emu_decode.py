@@ -19,7 +19,9 @@ def check(qoi, w, h, src_ch, target=0, flip=False, expect_path=None, **kw):
     if not np.array_equal(px[0], ref):
         bad = int(np.nonzero(px[0] != ref)[0][0]) // tgt
         raise AssertionError(f"{w}x{h} src {src_ch} -> {tgt} flip={flip}: first wrong pixel {bad} (path {path})")
-    if expect_path is not None:
+    if expect_path == 'serial':
+        assert path[0] >= 100
+    elif expect_path is not None:
         assert path[0] == expect_path
     return path[0]
 
@@ -105,7 +107,7 @@ def test_forced_sequential_kernel():
             raw = synth.generate(kind, w, h, ch)
             q = Oracle.encode(raw, w, h, ch)
             for target in (3, 4):
-                check(q, w, h, ch, target=target, flip=True, force_serial=True, expect_path=1)
+                check(q, w, h, ch, target=target, flip=True, force_serial=True, expect_path='serial')
 
 
 def test_batch_decode():
@@ -154,3 +156,33 @@ def test_stream_decoder_state_by_state():
             assert np.array_equal(oa[: ra[2]], ob[: rb[2]])
             assert a.s.run == b.s.run and bytes(a.s.prev) == bytes(b.s.prev) and bytes(a.s.seen) == bytes(b.s.seen)
             off += ra[1]
+
+
+def test_alpha_changing_index_ops_converge_in_retry_rounds():
+    """INDEX ops that change alpha refute the round-0 speculation; the retry rounds learn the alphas and converge
+    without the sequential kernel (path = number of rounds used, < 100)."""
+    for kind in ("hash_collide", "wrap", "alpha_toggle", "palette", "photo"):
+        for (w, h) in ((96, 64), (200, 150)):
+            raw = synth.generate(kind, w, h, 4)
+            q = Oracle.encode(raw, w, h, 4)
+            for target in (4, 3):
+                ref = Oracle.decode(q, target)
+                px, path = E.decode(q, w, h, target, seed=w)
+                assert np.array_equal(px[0], ref), (kind, w, h, target, path)
+                assert path[0] < 100, (kind, w, h, path)
+
+
+def test_restart_of_the_sequential_kernel_mid_stream():
+    """A stream that no retry round can verify (INDEX of a never-written slot late in the stream): the sequential
+    kernel resumes behind the last verified tile instead of at the image start."""
+    w, h = 120, 90
+    raw = synth.generate("photo", w, h, 3)
+    q = Oracle.encode(raw, w, h, 3)
+    body = q[14:-8].copy()
+    # overwrite an op near the end with INDEX 9 followed by the same bytes: slot 9 may or may not have been written,
+    # so check against the oracle rather than against `raw`
+    cut = body.size - 300
+    bad = np.concatenate([q[:14], body[:cut], np.array([9, 0x3F, 0x11], np.uint8), body[cut:], q[-8:]])
+    ref = Oracle.decode(bad, 3)
+    px, path = E.decode(bad, w, h, 3, seed=2)
+    assert np.array_equal(px[0], ref), path

@@ -190,3 +190,20 @@ def test_stream_decoder_sweep(ctx, ch):  # stream_test.cpp:204-252, every buffer
         if size % 4 == 1:
             px, _ = H.stream_decode(dec, size, f["qoi_incomplete"])
             assert px.size != f["raw"].size and np.array_equal(px, f["raw"][: px.size]), size
+
+
+def test_alpha_changing_index_ops_use_retry_rounds_not_the_sequential_kernel(ctx):
+    """decode_status path: 0 = first pass verified, 1..4 = retry rounds used, >= 100 = sequential kernel."""
+    import torch
+
+    for kind in ("hash_collide", "wrap", "alpha_toggle"):
+        w, h, ch = 1920, 1080, 4
+        raw = synth.generate(kind, w, h, ch)
+        q = Oracle.encode(raw, w, h, ch)
+        d_q = torch.from_numpy(q).cuda()
+        d_out = torch.zeros(w * h * ch, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        ctx.decode_dev(d_q, q.size, w, h, ch, 0, 0, False, d_out, d_out.numel(), st)
+        path = ctx.decode_status(st)
+        assert np.array_equal(d_out.cpu().numpy(), raw), kind
+        assert 0 < path < 100, (kind, path)
