@@ -11,7 +11,7 @@ import re
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-SO_PATH = os.path.join(PKG, "libqoipp_b200.so")
+SO_PATH = os.environ.get("QOIPP_B200_SO", os.path.join(PKG, "libqoipp_b200.so"))  # override: A/B builds during development
 HEADER = os.path.join(ROOT, "include", "qoipp_b200.h")
 
 u8p = C.POINTER(C.c_uint8)

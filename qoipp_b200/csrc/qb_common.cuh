@@ -14,7 +14,10 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #define QB_GRID_SYNC() cooperative_groups::this_grid().sync()
-#define QB_SPIN_YIELD() __nanosleep(32)
+#ifndef QB_SPIN_NS
+#define QB_SPIN_NS 0  // measured (tools/ab_probe.py): 0 / 32 / 100 / 250 / 600 ns -> decode 4K 272 / 283 / 287 / 289 / 296 us
+#endif
+#define QB_SPIN_YIELD() __nanosleep(QB_SPIN_NS)
 #define QB_DYN_SMEM qb_dyn_smem
 extern __shared__ __align__(128) unsigned char qb_dyn_smem[];
 #endif
@@ -178,6 +181,26 @@ namespace qb
 
     __device__ __forceinline__ unsigned lanemask_lt(unsigned lane) { return (1u << lane) - 1u; }
     __device__ __forceinline__ unsigned lanemask_gt(unsigned lane) { return lane == 31 ? 0u : ~((2u << lane) - 1u); }
+
+    // lanes of the warp whose (6-bit) slot equals this lane's, among the `active` ones.  Measured on B200 (tools/ab_probe.py):
+    // seven ballots instead of one __match_any_sync are no faster (4K RGB 129 vs 131 us, 8K RGBA 478 vs 459 us): the
+    // vote pipe (ADU) is already the busiest one, so the single MATCH instruction stays.
+    __device__ __forceinline__ unsigned match_slot(bool active, unsigned slot)
+    {
+#ifndef QB_MATCH_BY_BALLOTS
+        const unsigned lane = threadIdx.x & 31u;
+        const unsigned m    = __match_any_sync(kFull, active ? slot : 64u + lane);
+        return active ? m : 0u;
+#else
+        unsigned m = __ballot_sync(kFull, active);
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const unsigned v = __ballot_sync(kFull, (slot >> b) & 1u);
+            m &= ((slot >> b) & 1u) ? v : ~v;
+        }
+        return active ? m : 0u;
+#endif
+    }
 
     // bytewise (mod 256) subtract / add on packed pixels
     __device__ __forceinline__ unsigned sub4(unsigned a, unsigned b)

@@ -20,7 +20,10 @@ namespace H = qb::host;
 
 namespace
 {
-    constexpr int kEncK = 8;  // pixels per thread per tile: tile = 2048 pixels
+#ifndef QB_ENC_K
+#define QB_ENC_K 8
+#endif
+    constexpr int kEncK = QB_ENC_K;  // pixels per thread per tile: tile = 256 * K pixels
 
     int32_t cuda_code(cudaError_t e)
     {
