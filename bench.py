@@ -342,6 +342,14 @@ def main():
         dom = "decode_kernel" if dec_ms_max >= enc_ms_max else "encode_kernel"
         dom_ms = max(dec_ms_max, enc_ms_max) / args.steps
         achieved = alg / (dom_ms * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel, per launch, from the committed ncu --set full capture of this workload
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tr.get("workload") == args.workload and dom in tr["kernels"]:
+                traffic = int(tr["kernels"][dom]["dram_bytes_read"] + tr["kernels"][dom]["dram_bytes_write"])
+        except Exception:
+            traffic = None
         line = {
             "metric": "raw_pixel_GBps_encode_decode", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak",
@@ -352,7 +360,7 @@ def main():
             "encode_GBps": round(enc_gbps, 3), "decode_GBps": round(dec_gbps, 3),
             "encode_ms": round(enc_ms_max / args.steps, 5), "decode_ms": round(dec_ms_max / args.steps, 5),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes": alg, "encode_frac": round((alg / (enc_ms_max / args.steps * 1e-3) / 1e9) / peak, 5),
                          "decode_frac": round((alg / (dec_ms_max / args.steps * 1e-3) / 1e9) / peak, 5)},
             "e2e": {"value": round(e2e_gbps, 3), "unit": "GB/s", "h2d_bytes_per_step": (raw_one + e2e_enc) * e2e_imgs,
