@@ -1,0 +1,87 @@
+"""GPU (-m gpu): BASELINE.json configs at their full sizes, checked through size-independent properties
+(encode -> decode returns the input bit for bit; per-image sizes of identical images agree; a prefix of the stream equals
+the oracle's encoding of the same prefix of rows)."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import Oracle
+from qoipp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from qoipp_b200 import api
+
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def test_config3_16384x16384_rgba_roundtrip(ctx):
+    """configs[2]: single 16384x16384 RGBA image (noise: literal ops only, worst case for the speculative parse)."""
+    import torch
+
+    w = h = 16384
+    block = synth.generate("noise", 8192, 2048, 4)  # 64 MiB of noise, tiled: content class is what matters
+    d_block = torch.from_numpy(block).cuda()
+    d_raw = d_block.repeat((w * h) // (8192 * 2048))
+    assert d_raw.numel() == w * h * 4
+    cap = 5 * w * h + 22
+    d_q = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.encode_dev(d_raw, w, h, 4, 0, d_q, cap, st)
+    n, ok = ctx.encode_status(st)
+    assert ok and n > w * h * 4  # noise expands
+    # the first rows of the stream are what the oracle produces for the same rows (the codec is causal)
+    rows = 64
+    ref = Oracle.encode(d_raw[: w * rows * 4].cpu().numpy(), w, rows, 4)
+    got = d_q[: ref.size - 8].cpu().numpy()
+    assert np.array_equal(got[14:], ref[14:-8])
+    d_out = torch.zeros(w * h * 4, dtype=torch.uint8, device="cuda")
+    ctx.decode_dev(d_q, n, w, h, 4, 0, 0, False, d_out, d_out.numel(), st)
+    assert ctx.decode_status(st) == 0
+    assert torch.equal(d_out, d_raw)
+
+
+def test_config4_batch_8192_images_512x512_rgba(ctx):
+    """configs[3] on one GPU: 8192 images of 512x512 RGBA, 64 distinct contents replicated on the device."""
+    import torch
+
+    w = h = 512
+    B, distinct = 8192, 64
+    imgs = []
+    for k in range(distinct):
+        rgb = synth.generate("photo", w, h, 3, seed=0x51F0 + k).reshape(-1, 3)
+        imgs.append(np.concatenate([rgb, np.full((rgb.shape[0], 1), 255, np.uint8)], axis=1).reshape(-1))
+    d_src = torch.from_numpy(np.stack(imgs)).cuda()          # (64, raw)
+    d_raw = d_src.repeat(B // distinct, 1).reshape(-1)        # image k has content k % 64
+    raw_one = w * h * 4
+    stride = (5 * w * h + 22 + 255) // 256 * 256
+    d_q = torch.empty(stride * B, dtype=torch.uint8, device="cuda")
+    d_written = torch.zeros(B, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.encode_batch_dev(d_raw, raw_one, B, w, h, 4, 0, d_q, stride, stride, d_written, st)
+    torch.cuda.synchronize()
+    sizes = d_written.cpu().numpy()
+    assert np.array_equal(sizes, np.tile(sizes[:distinct], B // distinct))  # identical images, identical sizes
+    for k in (0, 17, 63):
+        ref = Oracle.encode(imgs[k], w, h, 4)
+        assert sizes[k] == ref.size
+        assert np.array_equal(d_q[(k + 128) * stride: (k + 128) * stride + ref.size].cpu().numpy(), ref)
+    # pack the streams back to back and decode the whole batch
+    offs = np.zeros(B + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum(sizes.astype(np.uint64))
+    idx = torch.arange(stride, device="cuda")
+    packed = torch.empty(int(offs[-1]) + 64, dtype=torch.uint8, device="cuda")
+    view = d_q.view(B, stride)
+    for k in range(distinct):  # images with equal content have equal size: copy them group-wise
+        rows = view[k::distinct, : int(sizes[k])]
+        starts = torch.from_numpy(offs[k:-1:distinct].astype(np.int64)).cuda()
+        dst = (starts[:, None] + idx[None, : int(sizes[k])]).reshape(-1)
+        packed[dst] = rows.reshape(-1)
+    d_out = torch.zeros(raw_one * B, dtype=torch.uint8, device="cuda")
+    ctx.decode_batch_dev(packed, offs, w, h, 4, 0, 0, d_out, raw_one, st)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out, d_raw)
