@@ -698,6 +698,26 @@ namespace qb
                 const unsigned cn   = min(pch, total - c0);
                 uint8_t*       gdst = out + (pix_base + c0) * tgt;
                 const unsigned sh   = (unsigned)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+                if (total <= pch && tgt == 4 && (sh & 3u) == 0) {
+                    // common case: the whole tile fits one staging round and pixels are word aligned
+                    unsigned* s32 = reinterpret_cast<unsigned*>(stg + sh);
+                    for (unsigned k = tid; k < n_ops; k += kDecThreads) {
+                        const unsigned meta = sm.op_meta[k], val = sm.op_val[k];
+                        const unsigned p0 = meta & 0x1FFFFu, np1 = (meta >> 17) & 63u;
+                        if (p0 < total) s32[p0] = val;
+                        if (np1)  // OP_RUN, clamped to the image (simple.cpp:158)
+                            for (unsigned j = 1; j <= np1 && p0 + j < total; ++j) s32[p0 + j] = val;
+                    }
+                } else if (total <= pch && tgt == 3) {
+                    for (unsigned k = tid; k < n_ops; k += kDecThreads) {
+                        const unsigned meta = sm.op_meta[k], val = sm.op_val[k];
+                        const unsigned p0 = meta & 0x1FFFFu, np1 = (meta >> 17) & 63u;
+                        for (unsigned j = 0; j <= np1 && p0 + j < total; ++j) {
+                            unsigned char* d = stg + sh + (p0 + j) * 3u;
+                            d[0] = (unsigned char)val, d[1] = (unsigned char)(val >> 8), d[2] = (unsigned char)(val >> 16);
+                        }
+                    }
+                } else
                 for (unsigned k = tid; k < n_ops; k += kDecThreads) {
                     const unsigned meta = sm.op_meta[k];
                     const unsigned p0 = meta & 0x1FFFFu, p1 = p0 + ((meta >> 17) & 63u) + 1u;  // tile-relative pixel range
