@@ -320,7 +320,7 @@ extern "C"
         uint8_t*       d_out = mapped_host(h_out);
         if (!d_in) {
             QB_CUDA(c->stage_in.reserve(raw_size + 16));
-            QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_raw, raw_size, cudaMemcpyHostToDevice, s));
+            QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_raw, raw_size, cudaMemcpyDefault, s));
             d_in = static_cast<uint8_t*>(c->stage_in.p);
         }
         const bool staged_out = d_out == nullptr;
@@ -331,7 +331,7 @@ extern "C"
         if (int32_t e = qoipp_b200_encode_dev(c, d_in, desc, d_out, cap, s)) return e;
         if (int32_t e = qoipp_b200_encode_status(c, s, written, complete)) return e;
         if (staged_out && *written) {
-            QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, *written, cudaMemcpyDeviceToHost, s));
+            QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, *written, cudaMemcpyDefault, s));
             QB_CUDA(cudaStreamSynchronize(s));
         }
         return 0;
