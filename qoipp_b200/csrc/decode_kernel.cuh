@@ -73,7 +73,13 @@ namespace qb
 
     constexpr int kFixWords = 32, kFixMax = kFixWords - 1;  // word 0: count | decode tag << 8; entries: pos | alpha << 16
 
-    constexpr int kDecThreads = 256, kDecWarps = 8, kDecSB = 8, kDecTB = kDecThreads * kDecSB;
+#ifndef QB_DEC_WARPS
+#define QB_DEC_WARPS 8
+#endif
+#ifndef QB_DEC_SB
+#define QB_DEC_SB 8
+#endif
+    constexpr int kDecWarps = QB_DEC_WARPS, kDecThreads = kDecWarps * 32, kDecSB = QB_DEC_SB, kDecTB = kDecThreads * kDecSB;
     constexpr int kDecDescWords = 72;
     constexpr int kDwParse = 0, kDwPix = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
 
@@ -856,33 +862,47 @@ namespace qb
 
         bool     stop = false;
         while (!stop && px < room) {
-            // stage kSerIn bytes from `pos` (zero padded in mode 0)
-            for (unsigned b = lane; b < kSerIn + 8; b += 32) sm.in[b] = pos + b < blen ? body[pos + b] : 0;
+            // stage kSerIn bytes from `pos` (zero padded past the end: simple.cpp:106)
+            for (unsigned b = lane; b < kSerIn + 16; b += 32) sm.in[b] = pos + b < blen ? body[pos + b] : 0;
             __syncwarp();
             if (lane == 0) {
-                unsigned ip = 0, op = 0;
+                // The next bytes of the stream live in a 64-bit register window refilled from prefetched words, so the
+                // tag -> length -> next tag chain never waits for shared memory.
+                const unsigned* in32 = reinterpret_cast<const unsigned*>(sm.in);
+                uint64_t        win  = (uint64_t)in32[0] | (uint64_t)in32[1] << 32;
+                unsigned        avail = 8, wnext = 4, n0 = in32[2], n1 = in32[3];
+                unsigned        ip = 0, op = 0;
                 while (op < kSerOut && px + op < room) {
                     if (run) {  // pending run (stream.cpp:335-339)
                         --run, sm.px[op++] = prev;
                         continue;
                     }
                     if (ip >= kSerIn) break;
-                    if (S.mode == 1 && pos + ip >= blen) { stop = true; break; }  // stream.cpp:341-344
-                    const unsigned tag = sm.in[ip], len = op_length(tag);
-                    if (S.mode == 1 && pos + ip + len > blen) { stop = true; break; }  // incomplete op is not consumed
-                    const OpInfo o = op_info(sm.in, ip, tag);
-                    unsigned     cur = prev;
-                    switch (o.kind) {
-                    case K_RGB: cur = o.data | (prev & 0xFF000000u); break;
-                    case K_RGBA: cur = o.data; break;
-                    case K_INDEX: cur = sm.table[o.lin]; break;
-                    case K_DIFF:
-                    case K_LUMA: cur = add4(prev, o.data); break;
-                    default: run = o.npix - 1; break;  // RUN: one pixel now, the rest pending
+                    const unsigned tag = (unsigned)win & 0xFFu, len = op_length(tag);
+                    if (S.mode == 1 && pos + ip + len > blen) { stop = true; break; }  // stream.cpp:341-392: incomplete op is not consumed
+                    const unsigned pay = (unsigned)(win >> 8);  // the four bytes after the tag
+                    unsigned       cur = prev;
+                    bool           is_run = false;
+                    if (tag == kOpRgb) cur = (pay & 0xFFFFFFu) | (prev & 0xFF000000u);  // simple.cpp:119-123
+                    else if (tag == kOpRgba) cur = pay;
+                    else if ((tag >> 6) == 0) cur = sm.table[tag & 63u];
+                    else if ((tag >> 6) == 1)
+                        cur = add4(prev, add4(((tag >> 4) & 3u) | ((tag >> 2) & 3u) << 8 | (tag & 3u) << 16, 0x00FEFEFEu));
+                    else if ((tag >> 6) == 2) {
+                        const unsigned rb = pay & 0xFFu, vg = ((tag & 63u) + 224u) & 255u;
+                        cur = add4(prev, ((vg + (rb >> 4) + 248u) & 255u) | vg << 8 | ((vg + (rb & 15u) + 248u) & 255u) << 16);
+                    } else {
+                        run = tag & 63u, is_run = true;  // RUN: one pixel now, the rest pending (simple.cpp:156-163)
                     }
-                    ip += len;
+                    ip += len, avail -= len;
+                    win = len == 8 ? 0 : win >> (8u * len);
+                    while (avail <= 4) {
+                        win |= (uint64_t)n0 << (8u * avail);
+                        avail += 4, n0 = n1, n1 = in32[wnext < (kSerIn + 16) / 4 ? wnext : 0];
+                        ++wnext;
+                    }
                     sm.px[op++] = cur;
-                    if (o.kind != K_RUN) sm.table[slot_of(cur)] = cur;  // simple.cpp:169
+                    if (!is_run) sm.table[slot_of(cur)] = cur;  // simple.cpp:169
                     prev = cur;
                 }
                 sm.ctl[0] = ip, sm.ctl[1] = op, sm.ctl[2] = stop;
