@@ -166,6 +166,41 @@ namespace qb
         return acc;
     }
 
+    // Same contract as warp_lookback, but `peek(p, st)` never waits: it returns tile p's word as it is now (st = ST_NONE when
+    // not published yet).  A round is accepted as soon as every predecessor CLOSER than the nearest inclusive one has
+    // published; farther tiles are never waited for, so a slow tile 30 places back does not hold this one up when a nearer
+    // tile already knows its inclusive prefix.
+    template <class T, class Peek, class Comb>
+    __device__ __forceinline__ T warp_lookback_lazy(unsigned t, T init, T empty, Peek peek, Comb comb)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        T              acc  = empty;
+        for (int base = (int)t - 1;; base -= 32) {
+            const int p = base - (int)lane;
+            T         v;
+            unsigned  st, incl, first;
+            for (;;) {
+                v = init, st = ST_INCL;
+                if (p >= 0) v = peek((unsigned)p, st);
+                incl  = __ballot_sync(kFull, st == ST_INCL);
+                first = incl ? (unsigned)__ffs((int)incl) - 1u : 32u;  // nearest inclusive predecessor of this window
+                const unsigned pending = __ballot_sync(kFull, st == ST_NONE) & (first >= 32u ? kFull : (1u << first) - 1u);
+                if (pending == 0) break;
+                QB_SPIN_YIELD();
+            }
+            if (st == ST_AGG_EMPTY || st == ST_NONE || lane > first) v = empty;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const T o = shfl_down_T(v, d);
+                if (lane + d < 32u) v = comb(o, v);
+            }
+            const T round = shfl_T(v, 0);
+            acc           = comb(round, acc);
+            if (incl) break;
+        }
+        return acc;
+    }
+
     // development aid (tools/phase_probe.py): with -DQB_TIMING thread 0 of every CTA stamps SM cycles at phase boundaries
     // into the padding words of its tile's carry record
 #if defined(QB_TIMING) && !defined(QB_EMU)

@@ -5,12 +5,14 @@
 
 #include "decode_kernel.cuh"
 #include "encode_kernel.cuh"
+#include "encode_ts.cuh"
 #include "host_util.hpp"
 
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -101,6 +103,7 @@ struct qoipp_b200_ctx {
     cudaStream_t own_stream = nullptr;
     bool     enc_trivial = false;  // last encode needed no launch (capacity below the header)
     bool     attrs_set   = false;
+    bool     force_general = false;  // QOIPP_B200_GENERAL=1: always the general kernels (A/B measurements, tests)
     int      dec_coresident = 148;  // CTAs of decode_finish_kernel that fit on the device at once
 
     // reserves `count` consecutive epochs and returns with `epoch` = the first; the carry buffer (and the tagged
@@ -144,6 +147,8 @@ namespace
         cudaError_t e;
         if ((e = allow_smem(encode_kernel<3, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
         if ((e = allow_smem(encode_kernel<4, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
+        if ((e = allow_smem(encode_ts_kernel<3>, sizeof(TsSmem<3>))) != cudaSuccess) return e;
+        if ((e = allow_smem(encode_ts_kernel<4>, sizeof(TsSmem<4>))) != cudaSuccess) return e;
         if ((e = dec_set_attrs()) != cudaSuccess) return e;
         int per_sm = 0;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_finish_kernel, kDecThreads, sizeof(DecSmem))) != cudaSuccess) return e;
@@ -172,8 +177,14 @@ namespace
                           uint32_t flags, const EncState* d_init, cudaStream_t s)
     {
         QB_CUDA(set_attrs(c));
-        constexpr uint64_t T = (uint64_t)kEncThreads * kEncK;
-        const uint64_t     tiles = (n_pixels + T - 1) / T;
+        // Thread-serial kernel (encode_ts.cuh) for the plain one-shot case: nothing can be refused (capacity >= worst size,
+        // util.hpp:240-246 never triggers), no carried state, every image 16-byte aligned.  Everything else -- partial
+        // buffers, the resumable form, unaligned spans -- takes the general kernel.
+        const bool ts = flags == 0 && d_init == nullptr && out_cap >= n_pixels * (ch + 1) + H::kHeaderSize + H::kMarkerSize &&
+                        (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && (n_images == 1 || (in_stride & 15u) == 0) &&
+                        !c->force_general;
+        const uint64_t T     = ts ? (uint64_t)kTsT : (uint64_t)kEncThreads * kEncK;
+        const uint64_t tiles = (n_pixels + T - 1) / T;
         if (tiles * n_images >= (1ull << 31)) return H::TooBig;
         QB_CUDA(c->results.reserve(sizeof(EncResult) * n_images));
         QB_CUDA(c->tickets.reserve(64, true));
@@ -187,9 +198,14 @@ namespace
         P.results    = static_cast<EncResult*>(c->results.p);
         P.desc       = static_cast<uint64_t*>(c->carry.p);
         P.ticket     = static_cast<uint32_t*>(c->tickets.p);
-        const dim3 grid((unsigned)(tiles * n_images)), block(kEncThreads);
-        if (ch == 3) encode_kernel<3, kEncK><<<grid, block, sizeof(EncSmem<kEncK>), s>>>(P);
-        else encode_kernel<4, kEncK><<<grid, block, sizeof(EncSmem<kEncK>), s>>>(P);
+        const dim3 grid((unsigned)(tiles * n_images));
+        if (ts) {
+            if (ch == 3) encode_ts_kernel<3><<<grid, dim3(kTsThreads), sizeof(TsSmem<3>), s>>>(P);
+            else encode_ts_kernel<4><<<grid, dim3(kTsThreads), sizeof(TsSmem<4>), s>>>(P);
+        } else {
+            if (ch == 3) encode_kernel<3, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
+            else encode_kernel<4, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
+        }
         QB_CUDA(cudaGetLastError());
         return 0;
     }
@@ -256,6 +272,7 @@ extern "C"
             return cuda_code(e);
         }
         c->sm_count = prop.multiProcessorCount;
+        if (const char* g = std::getenv("QOIPP_B200_GENERAL")) c->force_general = g[0] == '1';
         *out        = c;
         return 0;
     }

@@ -5,6 +5,7 @@
 
 #include "../../qoipp_b200/csrc/decode_kernel.cuh"
 #include "../../qoipp_b200/csrc/encode_kernel.cuh"
+#include "../../qoipp_b200/csrc/encode_ts.cuh"
 #include "../../qoipp_b200/csrc/host_util.hpp"
 
 #include <vector>
@@ -20,8 +21,19 @@ namespace
                     [=] { encode_kernel<CH, K>(P); }, resident, seed);
     }
 
+    template <int CH>
+    void run_encode_ts(const EncParams& P, int resident, uint64_t seed)
+    {
+        emu::launch(dim3(P.tiles_per_image * P.n_images), dim3(kTsThreads), sizeof(TsSmem<CH>) + 128,
+                    [=] { encode_ts_kernel<CH>(P); }, resident, seed);
+    }
+
+    // K == kTsK selects the thread-serial kernel (encode_ts.cuh), any other K the general kernel with K pixels per lane
+    uint64_t tile_pixels(int K) { return K == kTsK ? (uint64_t)kTsT : (uint64_t)kEncThreads * K; }
+
     void dispatch_encode(const EncParams& P, int ch, int K, int resident, uint64_t seed)
     {
+        if (K == kTsK) return ch == 3 ? run_encode_ts<3>(P, resident, seed) : run_encode_ts<4>(P, resident, seed);
 #define QB_CASE(CHV, KV) if (ch == CHV && K == KV) return run_encode<CHV, KV>(P, resident, seed);
         QB_CASE(3, 1) QB_CASE(4, 1) QB_CASE(3, 2) QB_CASE(4, 2) QB_CASE(3, 8) QB_CASE(4, 8)
 #undef QB_CASE
@@ -46,7 +58,7 @@ extern "C"
         P.in = raw; P.out = out;
         P.n_pixels = (uint64_t)w * h;
         P.in_stride = raw_stride; P.out_stride = out_stride; P.out_cap = cap;
-        const uint64_t T = (uint64_t)kEncThreads * K;
+        const uint64_t T = tile_pixels(K);
         P.tiles_per_image = (uint32_t)((P.n_pixels + T - 1) / T);
         P.n_images = n_images; P.epoch = 7; P.flags = 0;
         host::write_header(d, P.header);

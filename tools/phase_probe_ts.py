@@ -1,0 +1,38 @@
+"""Development aid: per-tile phase timing of encode_ts_kernel with the -DQB_TIMING build (libqoipp_b200_timing.so)."""
+import ctypes as C, sys
+import numpy as np, torch
+sys.path.insert(0, ".")
+from qoipp_b200 import synth
+from qoipp_b200._lib import Desc
+
+L = C.CDLL("qoipp_b200/libqoipp_b200_timing.so")
+ctx = C.c_void_p(); assert L.qoipp_b200_ctx_create(0, C.byref(ctx)) == 0
+st = torch.cuda.current_stream().cuda_stream
+names = ["ticket+init", "loads+W1", "merge", "lookback table/run", "encode loop", "scan+barrier", "compaction(w0)", "byte lookback", "copy-out"]
+T = 4096
+for kind, w, h, ch in [("photo", 3840, 2160, 3), ("photo", 7680, 4320, 4)]:
+    raw = synth.generate(kind, w, h, 3)
+    if ch == 4: raw = np.concatenate([raw.reshape(-1, 3), np.full((w * h, 1), 255, np.uint8)], axis=1).reshape(-1)
+    d_raw = torch.from_numpy(raw).cuda(); cap = (ch + 1) * w * h + 22
+    d_out = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        assert L.qoipp_b200_encode_dev(ctx, C.c_void_p(d_raw.data_ptr()), C.byref(Desc(w, h, ch, 0)), C.c_void_p(d_out.data_ptr()), C.c_uint64(cap), C.c_void_p(st)) == 0
+    torch.cuda.synchronize()
+    p, n = C.c_void_p(), C.c_uint64()
+    L.qoipp_b200_debug_carry(ctx, C.byref(p), C.byref(n))
+    ntiles = (w * h + T - 1) // T
+    buf = torch.empty(ntiles * 72 * 8, dtype=torch.uint8, device="cuda")
+    C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(buf.data_ptr()), p, C.c_size_t(buf.numel()), 3)
+    words = buf.cpu().numpy().view(np.uint32).reshape(ntiles, 144)
+    t = words[:, 132:141].astype(np.int64)
+    d = np.diff(np.concatenate([np.zeros((ntiles, 1), np.int64), t], axis=1), axis=1)
+    mid = slice(ntiles // 4, 3 * ntiles // 4)
+    print(f"{kind} {w}x{h}x{ch}: tiles {ntiles}; cycles per phase (middle half of tiles), total median {np.median(t[mid, -1]):.0f} cyc")
+    for i, nm in enumerate(names):
+        print(f"   {nm:20s} median {np.median(d[mid, i]):8.0f}  p10 {np.percentile(d[mid, i], 10):8.0f}  p90 {np.percentile(d[mid, i], 90):8.0f}")
+    ns0, ns1 = words[:, 142].astype(np.int64), words[:, 143].astype(np.int64)
+    base = ns0.min()
+    print("   start ns of tiles 0,1,2,591,592,593,1000,last:", [(int(ns0[i] - base)) for i in (0, 1, 2, 591, 592, 593, 1000, ntiles - 1)])
+    print("   end   ns of tiles 0,1,2,591,592,593,1000,last:", [(int(ns1[i] - base)) for i in (0, 1, 2, 591, 592, 593, 1000, ntiles - 1)])
+    dur = (ns1 - ns0)
+    print(f"   tile lifetime ns: median {np.median(dur):.0f} p10 {np.percentile(dur,10):.0f} p90 {np.percentile(dur,90):.0f}")
