@@ -50,6 +50,8 @@ namespace qb
         EncResult*      results;     // [n_images]
         uint64_t*       desc;        // [n_images * tiles_per_image][kEncDescWords]
         uint32_t*       ticket;
+        uint32_t*       scratch;     // encode_ts_kernel: per-tile records between its encode and copy roles
+        uint32_t        lag;         // encode_ts_kernel: ticket distance between the two roles of a tile
     };
 
     constexpr int kEncWarps = 8, kEncThreads = kEncWarps * 32;

@@ -18,9 +18,14 @@
 //   W2     chunk for "differs, no table hit" (DIFF / LUMA / RGB / RGBA) for all 32 pixels -- table independent, so
 //          it runs between publishing the tile's words and waiting for the predecessors';
 //   W3     the reference loop proper: probe + store per differing pixel, run counter, final chunk per pixel;
-//   emit   prefix sum of the per-thread byte counts, chunks appended through a 64-bit register window into the
-//          tile's staging bytes (32-bit stores; the words shared by two threads are merged with atomicOr),
-//          realigned 16-byte copy-out.
+//   W3     the reference loop proper: probe + store per differing pixel, run counter, final chunk per pixel, appended
+//          through a 64-bit register window to the thread's word-aligned slice of the tile's SCRATCH record in global
+//          memory ([word][thread], coalesced); the tile's byte count is published and the CTA is done with the tile;
+//   copy   `lag` tickets later some CTA (whose own encode work is finished) turns that record into the final bytes:
+//          look back over the byte counts -- by then every predecessor has long published, nobody waits for a slow
+//          neighbour --, prefix-sum the 128 per-thread counts, funnel-shift the slices into one contiguous run in
+//          shared memory, realigned 16-byte copy-out.  Measured: with the byte carry inside the encode pass every tile
+//          synchronised to the slowest of its 32 predecessors (6.2k of 33k cycles per tile waiting, 4 CTAs per SM).
 #pragma once
 
 #include "encode_kernel.cuh"
@@ -31,7 +36,7 @@ namespace qb
 #define QB_TS_THREADS 128
 #endif
 #ifndef QB_TS_CTAS
-#define QB_TS_CTAS (512 / QB_TS_THREADS)
+#define QB_TS_CTAS (768 / QB_TS_THREADS)
 #endif
     constexpr int kTsThreads = QB_TS_THREADS, kTsWarps = kTsThreads / 32, kTsK = 32, kTsT = kTsThreads * kTsK;
     constexpr int kTsHalves = kTsThreads / 64;  // the merge scans ranges of 64 threads concurrently
@@ -40,14 +45,14 @@ namespace qb
     template <int CH>
     struct TsSmem {
         static constexpr int kPrivWords = kTsK * (CH + 1) / 4 + 1;  // per thread: its chunks, word aligned (+ the partial word)
-        alignas(16) unsigned tab[64 * kTsThreads];  // [slot][thread]; after the encode loop: the tile's staging bytes
-        unsigned priv[kPrivWords * kTsThreads];     // [word][thread]
+        static constexpr int kScrWords  = (kPrivWords + 1) * kTsThreads;  // scratch record of a tile: [word][thread], then the counts
+        alignas(16) unsigned tab[64 * kTsThreads];  // [slot][thread]; in the copy phase: the tile's staging bytes
         unsigned endv[kTsHalves][64];  // last writer per slot in each range of 64 threads (sentinel = none)
         unsigned gin[kTsHalves][64];   // table on entry to each range
         unsigned wlast[kTsWarps];  // per warp: tile-local index + 1 of its last differing pixel, 0 = none
         unsigned wbytes[kTsWarps];
         uint64_t tile_off;
-        unsigned ticket, base62;
+        unsigned ticket, base62, tile_bytes;
     };
 
     // chunk of a pixel that differs from its predecessor and missed the table (simple.cpp:59-79, util.hpp:163-225):
@@ -70,22 +75,18 @@ namespace qb
         len   = alpha_ne ? 5u : (diff_ok ? 1u : (luma_ok ? 2u : 4u));
     }
 
+    // ---- encode role: tile `gt` (global tile index) -> scratch record + carry words
     template <int CH>
-    __global__ void __launch_bounds__(kTsThreads, QB_TS_CTAS) encode_ts_kernel(const EncParams P)
+    __device__ __forceinline__ void ts_encode_tile(const EncParams& P, TsSmem<CH>& sm, unsigned gt)
     {
         using S          = TsSmem<CH>;
         constexpr int K  = kTsK, NT = kTsThreads, T = kTsT;
-        S&            sm = *reinterpret_cast<S*>(QB_DYN_SMEM);
         const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
         [[maybe_unused]] const long long qb_t0 = QB_T0();
 
-        if (tid == 0) sm.ticket = atomicInc(P.ticket, P.tiles_per_image * P.n_images - 1u);
-        __syncthreads();
-
-        const unsigned  img        = sm.ticket / P.tiles_per_image;
-        const unsigned  t          = sm.ticket % P.tiles_per_image;
+        const unsigned  img        = gt / P.tiles_per_image;
+        const unsigned  t          = gt % P.tiles_per_image;
         const uint8_t*  in_img     = P.in + (uint64_t)img * P.in_stride;
-        uint8_t*        out_img    = P.out + (uint64_t)img * P.out_stride;
         const uint64_t  N          = P.n_pixels;
         const uint64_t  tile_start = (uint64_t)t * T;
         const unsigned  n_here     = (unsigned)(N - tile_start < (uint64_t)T ? N - tile_start : (uint64_t)T);
@@ -282,7 +283,8 @@ namespace qb
             for (unsigned ww = 0; ww < w; ++ww) bf = max(bf, sm.wlast[ww]);
             r = bf ? (first - bf) % kRunLimit : (first + sm.base62 + kRunLimit - 1u) % kRunLimit;
         }
-        unsigned* const priv = sm.priv + tid;  // word j of this thread at priv[j * NT]: bank = thread, conflict free
+        unsigned* const scr  = P.scratch + (uint64_t)gt * S::kScrWords;
+        unsigned* const priv = scr + tid;  // word j of this thread at priv[j * NT]: a warp stores whole 128-byte lines
         unsigned        nw = 0, fill = 0, alo = 0, ahi = 0;  // whole words stored, bytes pending in alo (ahi: overflow of one append)
         {
             const unsigned* gin = sm.gin[tid >> 6];
@@ -328,69 +330,52 @@ namespace qb
         const unsigned total = nw * 4u + fill;
         QB_STAMP(desc, 68, 0, qb_t0);  // encode loop
 
-        // ================= carry (3): byte offsets =================
-        unsigned off;  // tile-relative offset of this thread's first byte
+        // ================= carry (3): the tile's byte count; the record is complete =================
+        priv[S::kPrivWords * NT] = total;
         {
-            unsigned inc = total;
+            unsigned sum = total;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned o = __shfl_up_sync(kFull, inc, d);
-                if ((int)lane >= d) inc += o;
-            }
-            off = inc - total;
-            if (lane == 31) sm.wbytes[w] = inc;
+            for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
+            if (lane == 0) sm.wbytes[w] = sum;
         }
-        __syncthreads();  // every thread is done with the table: its memory becomes the tile's staging bytes
-        unsigned tile_bytes = 0;
+        __syncthreads();  // every thread's scratch stores are issued
+        if (tid == 0) {
+            unsigned tile_bytes = 0;
 #pragma unroll
-        for (int ww = 0; ww < kTsWarps; ++ww) tile_bytes += sm.wbytes[ww];
-        if (tid == 0 && t > 0) st_word(desc + kWordBytes, pack_word(tile_bytes, ST_AGG, epoch));  // successors can go on
-        for (unsigned ww = 0; ww < w; ++ww) off += sm.wbytes[ww];
-        QB_STAMP(desc, 68, 1, qb_t0);  // scan + barrier
+            for (int ww = 0; ww < kTsWarps; ++ww) tile_bytes += sm.wbytes[ww];
+            __threadfence();  // the record before the word that announces it
+            st_word(desc + kWordBytes, pack_word(tile_bytes, ST_AGG, epoch));
+        }
+        QB_STAMP(desc, 68, 1, qb_t0);  // publish
+#if defined(QB_TIMING) && !defined(QB_EMU)
+        if (tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); reinterpret_cast<unsigned*>(desc + 71)[1] = (unsigned)ns; }
+#endif
+    }
 
-        // ================= compaction: private words -> the tile's contiguous bytes =================
-        unsigned char* const stage = reinterpret_cast<unsigned char*>(sm.tab);
-        if (total) {
-            // destination word m (from the word holding my first byte) = my bytes 4m - a .. 4m - a + 3: private words m - 1 and m
-            // funnel-shifted; only the first and the last destination word can be shared with a neighbour (byte stores)
-            const unsigned a = off & 3u, rs = 32u - a * 8u;
-            unsigned*      d32 = reinterpret_cast<unsigned*>(stage) + (off >> 2);
-            const unsigned nwp = (total + 3u) >> 2;      // private words holding bytes
-            const unsigned nd  = (total + a + 3u) >> 2;  // destination words touched
-            auto partial = [&](unsigned m, unsigned v) {
-                const unsigned b0 = m == 0 ? a : 0u, b1 = min(4u, total + a - 4u * m);
-                unsigned char* d = reinterpret_cast<unsigned char*>(d32 + m);
-#pragma unroll
-                for (unsigned bb = 0; bb < 4; ++bb)
-                    if (bb >= b0 && bb < b1) d[bb] = (unsigned char)(v >> (8u * bb));
-            };
-            unsigned lo = priv[0];
-            {
-                const unsigned v = __funnelshift_rc(0u, lo, rs);
-                if (a == 0 && total >= 4u) d32[0] = v;
-                else partial(0u, v);
-            }
-            unsigned m = 1;
-            for (; m + 4u < nd; m += 4u) {  // four whole words per round, loads first
-                unsigned h[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) h[i] = priv[(m + i) * NT];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    d32[m + i] = __funnelshift_rc(lo, h[i], rs);
-                    lo         = h[i];
-                }
-            }
-            for (; m < nd; ++m) {
-                const unsigned hi = m < nwp ? priv[m * NT] : 0u;
-                const unsigned v  = __funnelshift_rc(lo, hi, rs);
-                lo                = hi;
-                if (m + 1u < nd || ((total + a) & 3u) == 0) d32[m] = v;
-                else partial(m, v);
-            }
+    // ---- copy role: scratch record of tile `gt` -> the tile's bytes at their final place
+    template <int CH>
+    __device__ __forceinline__ void ts_copy_tile(const EncParams& P, TsSmem<CH>& sm, unsigned gt)
+    {
+        using S          = TsSmem<CH>;
+        constexpr int NT = kTsThreads;
+        const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+        [[maybe_unused]] const long long qb_t0 = QB_T0();
+        const unsigned  img     = gt / P.tiles_per_image;
+        const unsigned  t       = gt % P.tiles_per_image;
+        uint8_t*        out_img = P.out + (uint64_t)img * P.out_stride;
+        uint64_t*       desc    = P.desc + (uint64_t)gt * kEncDescWords;
+        const unsigned  epoch   = P.epoch;
+        const unsigned* scr     = P.scratch + (uint64_t)gt * S::kScrWords;
+        const unsigned* priv    = scr + tid;
+
+        if (tid == 0) {  // the encoder of this tile holds a lower ticket: it is running or done
+            sm.tile_bytes = (unsigned)word_payload(wait_word(desc + kWordBytes, epoch));
+            __threadfence();  // the word before the record it announces
         }
-        if (w == 0) {  // look back (32 predecessors per round): where the tile's bytes start
-            QB_STAMP(desc, 69, 0, qb_t0);  // compaction (warp 0)
+        __syncthreads();
+        const unsigned tile_bytes = sm.tile_bytes;
+        QB_STAMP(desc, 69, 1, qb_t0);  // copy: waited for the record
+        if (w == 0) {  // where the tile's bytes start: look back over the byte counts, 32 predecessors per round
             const uint64_t toff = warp_lookback_lazy<uint64_t>(
                 t, (uint64_t)kHeader, (uint64_t)0,
                 [&](unsigned p, unsigned& st) {
@@ -404,11 +389,69 @@ namespace qb
                 sm.tile_off = toff;
             }
         }
+        // per-thread byte counts -> offsets inside the tile
+        const unsigned total = __ldcg(priv + S::kPrivWords * NT);
+        unsigned       off;
+        {
+            unsigned inc = total;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(kFull, inc, d);
+                if ((int)lane >= d) inc += o;
+            }
+            off = inc - total;
+            if (lane == 31) sm.wbytes[w] = inc;
+        }
+        __syncthreads();
+        for (unsigned ww = 0; ww < w; ++ww) off += sm.wbytes[ww];
+        QB_STAMP(desc, 70, 0, qb_t0);  // copy: look-back (warp 0), counts, scan
+
+        // ================= compaction: the threads' word-aligned slices -> the tile's contiguous bytes =================
+        unsigned char* const stage = reinterpret_cast<unsigned char*>(sm.tab);
+        if (total) {
+            // destination word m (from the word holding my first byte) = my bytes 4m - a .. 4m - a + 3: slice words m - 1 and m
+            // funnel-shifted; only the first and the last destination word can be shared with a neighbour (byte stores)
+            const unsigned a = off & 3u, rs = 32u - a * 8u;
+            unsigned*      d32 = reinterpret_cast<unsigned*>(stage) + (off >> 2);
+            const unsigned nwp = (total + 3u) >> 2;      // slice words holding bytes
+            const unsigned nd  = (total + a + 3u) >> 2;  // destination words touched
+            auto partial = [&](unsigned m, unsigned v) {
+                const unsigned b0 = m == 0 ? a : 0u, b1 = min(4u, total + a - 4u * m);
+                unsigned char* d = reinterpret_cast<unsigned char*>(d32 + m);
+#pragma unroll
+                for (unsigned bb = 0; bb < 4; ++bb)
+                    if (bb >= b0 && bb < b1) d[bb] = (unsigned char)(v >> (8u * bb));
+            };
+            unsigned lo = __ldcg(priv);
+            {
+                const unsigned v = __funnelshift_rc(0u, lo, rs);
+                if (a == 0 && total >= 4u) d32[0] = v;
+                else partial(0u, v);
+            }
+            unsigned m = 1;
+            for (; m + 4u < nd; m += 4u) {  // four whole words per round, loads first
+                unsigned h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __ldcg(priv + (m + i) * NT);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    d32[m + i] = __funnelshift_rc(lo, h[i], rs);
+                    lo         = h[i];
+                }
+            }
+            for (; m < nd; ++m) {
+                const unsigned hi = m < nwp ? __ldcg(priv + m * NT) : 0u;
+                const unsigned v  = __funnelshift_rc(lo, hi, rs);
+                lo                = hi;
+                if (m + 1u < nd || ((total + a) & 3u) == 0) d32[m] = v;
+                else partial(m, v);
+            }
+        }
         __syncthreads();
 
+        QB_STAMP(desc, 70, 1, qb_t0);  // copy: compaction
         // ================= realigned 16-byte copy-out =================
         const uint64_t tile_off   = sm.tile_off;
-        QB_STAMP(desc, 69, 1, qb_t0);  // byte look-back + barrier
         const unsigned tile_total = tile_bytes;
         if (tile_total) {
             uint8_t*        dst  = out_img + tile_off;
@@ -428,17 +471,35 @@ namespace qb
             if (tid < tile_total - done) dst[done + tid] = stage[done + tid];
         }
         if (t == 0 && tid < kHeader) out_img[tid] = P.header[tid];
-        QB_STAMP(desc, 70, 0, qb_t0);  // copy-out
-#if defined(QB_TIMING) && !defined(QB_EMU)
-        if (tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); reinterpret_cast<unsigned*>(desc + 71)[1] = (unsigned)ns; }
-#endif
         if (t == P.tiles_per_image - 1 && tid == 0) {  // end marker (util.hpp:151-161) and the result
             const uint64_t written = tile_off + tile_total;
             for (unsigned b = 0; b < kMarker; ++b) out_img[written + b] = b == kMarker - 1 ? 1 : 0;
             EncResult* res = P.results + img;
             res->written   = written + kMarker;
             res->complete  = 1;
-            res->processed = N;
+            res->processed = P.n_pixels;
         }
+        QB_STAMP(desc, 69, 0, qb_t0);  // copy role
+    }
+
+    // Grid = tiles + lag CTAs.  Ticket x (handed out in start order) encodes tile x (x < tiles).  A CTA that is done encoding --
+    // or has nothing to encode -- takes a copy ticket c (handed out in FINISHING order) and copies tile c - lag: at least c
+    // CTAs finished before it, so that tile's encoder started long ago and, `lag` finishers later, is done in practice; the
+    // copy role therefore finds every word it looks back on already published, and no tile waits for a slow neighbour.
+    // Every CTA a running one can wait for has started (tickets are issued in order), so the waits cannot deadlock.
+    template <int CH>
+    __global__ void __launch_bounds__(kTsThreads, QB_TS_CTAS) encode_ts_kernel(const EncParams P)
+    {
+        TsSmem<CH>& sm = *reinterpret_cast<TsSmem<CH>*>(QB_DYN_SMEM);
+        const unsigned n_tiles = P.tiles_per_image * P.n_images;
+        if (threadIdx.x == 0) sm.ticket = atomicInc(P.ticket, n_tiles + P.lag - 1u);
+        __syncthreads();
+        const unsigned x = sm.ticket;
+        if (x < n_tiles) ts_encode_tile<CH>(P, sm, x);
+        __syncthreads();  // the table's memory becomes the staging bytes
+        if (threadIdx.x == 0) sm.ticket = atomicInc(P.ticket + 1, n_tiles + P.lag - 1u);
+        __syncthreads();
+        const unsigned c = sm.ticket;
+        if (c >= P.lag) ts_copy_tile<CH>(P, sm, c - P.lag);
     }
 }  // namespace qb

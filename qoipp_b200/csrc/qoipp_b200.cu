@@ -97,6 +97,7 @@ struct qoipp_b200_ctx {
     DevBuf   state;       // EncState / DecState carry-in for the resumable calls
     DevBuf   aux;         // decode: per-image offsets and first-tile ids of a batch
     DevBuf   fix;         // decode: per-tile lists of alphas learned by the retry rounds
+    DevBuf   scratch;     // encode_ts_kernel: per-tile records between the encode and copy roles
     DevBuf   stage_in, stage_out;  // device staging of the host-pointer calls
     PinnedBuf h_result;   // pinned landing zone for result structs
     PinnedBuf h_pin_in, h_pin_out;
@@ -200,8 +201,14 @@ namespace
         P.ticket     = static_cast<uint32_t*>(c->tickets.p);
         const dim3 grid((unsigned)(tiles * n_images));
         if (ts) {
-            if (ch == 3) encode_ts_kernel<3><<<grid, dim3(kTsThreads), sizeof(TsSmem<3>), s>>>(P);
-            else encode_ts_kernel<4><<<grid, dim3(kTsThreads), sizeof(TsSmem<4>), s>>>(P);
+            const uint64_t scr_words = ch == 3 ? TsSmem<3>::kScrWords : TsSmem<4>::kScrWords;
+            if (tiles * n_images * scr_words * 4 > c->scratch.cap) QB_CUDA(cudaStreamSynchronize(s));  // an earlier launch may still use it
+            QB_CUDA(c->scratch.reserve(tiles * n_images * scr_words * 4));
+            P.scratch = static_cast<uint32_t*>(c->scratch.p);
+            P.lag     = (uint32_t)std::min<uint64_t>(tiles * n_images, (unsigned)c->sm_count);  // see encode_ts_kernel
+            const dim3 grid2(grid.x + P.lag);
+            if (ch == 3) encode_ts_kernel<3><<<grid2, dim3(kTsThreads), sizeof(TsSmem<3>), s>>>(P);
+            else encode_ts_kernel<4><<<grid2, dim3(kTsThreads), sizeof(TsSmem<4>), s>>>(P);
         } else {
             if (ch == 3) encode_kernel<3, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
             else encode_kernel<4, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
@@ -282,7 +289,7 @@ extern "C"
         if (!c) return 0;
         Guard g(c->device);
         cudaDeviceSynchronize();
-        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release();
+        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release(), c->scratch.release();
         c->stage_in.release(), c->stage_out.release();
         c->h_result.release(), c->h_pin_in.release(), c->h_pin_out.release();
         if (c->own_stream) cudaStreamDestroy(c->own_stream);

@@ -354,6 +354,7 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
 static inline unsigned __vsub4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) r |= (((a >> (8 * i)) - (b >> (8 * i))) & 255u) << (8 * i); return r; }
 static inline unsigned __vadd4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; ++i) r |= (((a >> (8 * i)) + (b >> (8 * i))) & 255u) << (8 * i); return r; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 template <typename T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
 

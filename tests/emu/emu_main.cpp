@@ -8,6 +8,7 @@
 #include "../../qoipp_b200/csrc/encode_ts.cuh"
 #include "../../qoipp_b200/csrc/host_util.hpp"
 
+#include <algorithm>
 #include <vector>
 
 using namespace qb;
@@ -24,8 +25,12 @@ namespace
     template <int CH>
     void run_encode_ts(const EncParams& P, int resident, uint64_t seed)
     {
-        emu::launch(dim3(P.tiles_per_image * P.n_images), dim3(kTsThreads), sizeof(TsSmem<CH>) + 128,
-                    [=] { encode_ts_kernel<CH>(P); }, resident, seed);
+        EncParams Q = P;
+        const unsigned n_tiles = P.tiles_per_image * P.n_images;
+        std::vector<uint32_t> scratch((size_t)n_tiles * TsSmem<CH>::kScrWords, 0xDEADBEEFu);
+        Q.scratch = scratch.data();
+        Q.lag     = std::min<unsigned>(n_tiles, (unsigned)(seed % 3 + 1));  // small lags: the copy role does have to wait here
+        emu::launch(dim3(n_tiles + Q.lag), dim3(kTsThreads), sizeof(TsSmem<CH>) + 128, [=] { encode_ts_kernel<CH>(Q); }, resident, seed);
     }
 
     // K == kTsK selects the thread-serial kernel (encode_ts.cuh), any other K the general kernel with K pixels per lane
@@ -64,10 +69,10 @@ extern "C"
         host::write_header(d, P.header);
         std::vector<uint64_t>  desc((size_t)P.tiles_per_image * n_images * kEncDescWords, 0);
         std::vector<EncResult> res(n_images);
-        uint32_t               ticket = 0;
-        P.desc = desc.data(); P.results = res.data(); P.ticket = &ticket; P.init_state = nullptr;
+        uint32_t               ticket[2] = { 0, 0 };
+        P.desc = desc.data(); P.results = res.data(); P.ticket = ticket; P.init_state = nullptr;
         dispatch_encode(P, ch, K, resident, seed);
-        if (ticket != 0) return -1;
+        if (ticket[0] != 0 || ticket[1] != 0) return -1;
         for (uint32_t i = 0; i < n_images; ++i) written[i] = res[i].written, complete[i] = (int)res[i].complete;
         return 0;
     }

@@ -8,7 +8,7 @@ from qoipp_b200._lib import Desc
 L = C.CDLL("qoipp_b200/libqoipp_b200_timing.so")
 ctx = C.c_void_p(); assert L.qoipp_b200_ctx_create(0, C.byref(ctx)) == 0
 st = torch.cuda.current_stream().cuda_stream
-names = ["ticket+init", "loads+W1", "merge", "lookback table/run", "encode loop", "scan+barrier", "compaction(w0)", "byte lookback", "copy-out"]
+names = ["ticket", "loads+W1", "merge", "lookback table/run", "encode loop", "publish"]
 T = 4096
 for kind, w, h, ch in [("photo", 3840, 2160, 3), ("photo", 7680, 4320, 4)]:
     raw = synth.generate(kind, w, h, 3)
@@ -24,12 +24,15 @@ for kind, w, h, ch in [("photo", 3840, 2160, 3), ("photo", 7680, 4320, 4)]:
     buf = torch.empty(ntiles * 72 * 8, dtype=torch.uint8, device="cuda")
     C.cdll.LoadLibrary("libcudart.so.12").cudaMemcpy(C.c_void_p(buf.data_ptr()), p, C.c_size_t(buf.numel()), 3)
     words = buf.cpu().numpy().view(np.uint32).reshape(ntiles, 144)
-    t = words[:, 132:141].astype(np.int64)
+    t = words[:, 132:138].astype(np.int64)
     d = np.diff(np.concatenate([np.zeros((ntiles, 1), np.int64), t], axis=1), axis=1)
     mid = slice(ntiles // 4, 3 * ntiles // 4)
     print(f"{kind} {w}x{h}x{ch}: tiles {ntiles}; cycles per phase (middle half of tiles), total median {np.median(t[mid, -1]):.0f} cyc")
     for i, nm in enumerate(names):
         print(f"   {nm:20s} median {np.median(d[mid, i]):8.0f}  p10 {np.percentile(d[mid, i], 10):8.0f}  p90 {np.percentile(d[mid, i], 90):8.0f}")
+    print(f"   copy role (own clock)  median {np.median(words[mid, 138]):8.0f}  p10 {np.percentile(words[mid, 138], 10):8.0f}  p90 {np.percentile(words[mid, 138], 90):8.0f}")
+    for nm, col in (("copy: wait record", 139), ("copy: lookback+scan", 140), ("copy: compaction", 141)):
+        print(f"   {nm:22s} median {np.median(words[mid, col]):8.0f}  p90 {np.percentile(words[mid, col], 90):8.0f}   (cumulative)")
     ns0, ns1 = words[:, 142].astype(np.int64), words[:, 143].astype(np.int64)
     base = ns0.min()
     print("   start ns of tiles 0,1,2,591,592,593,1000,last:", [(int(ns0[i] - base)) for i in (0, 1, 2, 591, 592, 593, 1000, ntiles - 1)])
