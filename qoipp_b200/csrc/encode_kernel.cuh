@@ -51,7 +51,8 @@ namespace qb
         uint64_t*       desc;        // [n_images * tiles_per_image][kEncDescWords]
         uint32_t*       ticket;
         uint32_t*       scratch;     // encode_ts_kernel: per-tile records between its encode and copy roles
-        uint32_t        lag;         // encode_ts_kernel: ticket distance between the two roles of a tile
+        uint32_t        lag;         // encode_ts_kernel: finished tiles between the two roles of a tile
+        uint32_t        ticket_base[2];  // encode_ts_kernel: values of ticket[0], ticket[1] at launch (never reset)
     };
 
     constexpr int kEncWarps = 8, kEncThreads = kEncWarps * 32;

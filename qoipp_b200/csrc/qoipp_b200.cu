@@ -104,6 +104,8 @@ struct qoipp_b200_ctx {
     cudaStream_t own_stream = nullptr;
     bool     enc_trivial = false;  // last encode needed no launch (capacity below the header)
     bool     attrs_set   = false;
+    uint32_t ts_ticket[2] = { 0, 0 };  // encode_ts_kernel: current values of its two ticket counters
+    uint32_t ts_lag = 512;
     bool     force_general = false;  // QOIPP_B200_GENERAL=1: always the general kernels (A/B measurements, tests)
     int      dec_coresident = 148;  // CTAs of decode_finish_kernel that fit on the device at once
 
@@ -148,8 +150,8 @@ namespace
         cudaError_t e;
         if ((e = allow_smem(encode_kernel<3, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
         if ((e = allow_smem(encode_kernel<4, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
-        if ((e = allow_smem(encode_ts_kernel<3>, sizeof(TsSmem<3>))) != cudaSuccess) return e;
-        if ((e = allow_smem(encode_ts_kernel<4>, sizeof(TsSmem<4>))) != cudaSuccess) return e;
+        if ((e = allow_smem(encode_ts_kernel<3>, kTsWarps * sizeof(TsWarpSmem))) != cudaSuccess) return e;
+        if ((e = allow_smem(encode_ts_kernel<4>, kTsWarps * sizeof(TsWarpSmem))) != cudaSuccess) return e;
         if ((e = dec_set_attrs()) != cudaSuccess) return e;
         int per_sm = 0;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_finish_kernel, kDecThreads, sizeof(DecSmem))) != cudaSuccess) return e;
@@ -201,14 +203,22 @@ namespace
         P.ticket     = static_cast<uint32_t*>(c->tickets.p);
         const dim3 grid((unsigned)(tiles * n_images));
         if (ts) {
-            const uint64_t scr_words = ch == 3 ? TsSmem<3>::kScrWords : TsSmem<4>::kScrWords;
-            if (tiles * n_images * scr_words * 4 > c->scratch.cap) QB_CUDA(cudaStreamSynchronize(s));  // an earlier launch may still use it
-            QB_CUDA(c->scratch.reserve(tiles * n_images * scr_words * 4));
+            const uint64_t n_tiles   = tiles * n_images;
+            const uint64_t scr_words = ch == 3 ? TsCfg<3>::kScrWords : TsCfg<4>::kScrWords;
+            if (n_tiles * scr_words * 4 > c->scratch.cap) QB_CUDA(cudaStreamSynchronize(s));  // an earlier launch may still use it
+            QB_CUDA(c->scratch.reserve(n_tiles * scr_words * 4));
             P.scratch = static_cast<uint32_t*>(c->scratch.p);
-            P.lag     = (uint32_t)std::min<uint64_t>(tiles * n_images, (unsigned)c->sm_count);  // see encode_ts_kernel
-            const dim3 grid2(grid.x + P.lag);
-            if (ch == 3) encode_ts_kernel<3><<<grid2, dim3(kTsThreads), sizeof(TsSmem<3>), s>>>(P);
-            else encode_ts_kernel<4><<<grid2, dim3(kTsThreads), sizeof(TsSmem<4>), s>>>(P);
+            P.lag     = (uint32_t)std::min<uint64_t>(n_tiles, c->ts_lag);  // see encode_ts_kernel
+            // persistent warps: one CTA slot per resident CTA; the ticket counters are never reset, every warp draws exactly
+            // one ticket beyond the last valid one
+            const uint64_t n_tickets = n_tiles + P.lag;
+            const unsigned n_ctas    = (unsigned)std::min<uint64_t>((n_tickets + kTsWarps - 1) / kTsWarps, (uint64_t)c->sm_count * QB_TS_CTAS);
+            P.ticket         = static_cast<uint32_t*>(c->tickets.p) + 8;
+            P.ticket_base[0] = c->ts_ticket[0], P.ticket_base[1] = c->ts_ticket[1];
+            c->ts_ticket[0] += (uint32_t)n_tickets + n_ctas * kTsWarps;
+            c->ts_ticket[1] += (uint32_t)n_tickets;
+            if (ch == 3) encode_ts_kernel<3><<<dim3(n_ctas), dim3(kTsThreads), kTsWarps * sizeof(TsWarpSmem), s>>>(P);
+            else encode_ts_kernel<4><<<dim3(n_ctas), dim3(kTsThreads), kTsWarps * sizeof(TsWarpSmem), s>>>(P);
         } else {
             if (ch == 3) encode_kernel<3, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
             else encode_kernel<4, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
@@ -280,6 +290,7 @@ extern "C"
         }
         c->sm_count = prop.multiProcessorCount;
         if (const char* g = std::getenv("QOIPP_B200_GENERAL")) c->force_general = g[0] == '1';
+        if (const char* g = std::getenv("QOIPP_B200_TS_LAG")) c->ts_lag = (uint32_t)std::max(1, std::atoi(g));  // development knob
         *out        = c;
         return 0;
     }

@@ -27,10 +27,13 @@ namespace
     {
         EncParams Q = P;
         const unsigned n_tiles = P.tiles_per_image * P.n_images;
-        std::vector<uint32_t> scratch((size_t)n_tiles * TsSmem<CH>::kScrWords, 0xDEADBEEFu);
+        std::vector<uint32_t> scratch((size_t)n_tiles * TsCfg<CH>::kScrWords, 0xDEADBEEFu);
+        uint32_t tickets[2] = { 1000u + (uint32_t)seed, 0xFFFFFFF0u };  // the counters never reset (and may wrap)
         Q.scratch = scratch.data();
         Q.lag     = std::min<unsigned>(n_tiles, (unsigned)(seed % 3 + 1));  // small lags: the copy role does have to wait here
-        emu::launch(dim3(n_tiles + Q.lag), dim3(kTsThreads), sizeof(TsSmem<CH>) + 128, [=] { encode_ts_kernel<CH>(Q); }, resident, seed);
+        Q.ticket = tickets; Q.ticket_base[0] = tickets[0]; Q.ticket_base[1] = tickets[1];
+        const unsigned n_ctas = std::min<unsigned>((n_tiles + Q.lag + kTsWarps - 1) / kTsWarps, (unsigned)resident);
+        emu::launch(dim3(n_ctas), dim3(kTsThreads), kTsWarps * sizeof(TsWarpSmem) + 128, [=] { encode_ts_kernel<CH>(Q); }, resident, seed);
     }
 
     // K == kTsK selects the thread-serial kernel (encode_ts.cuh), any other K the general kernel with K pixels per lane
