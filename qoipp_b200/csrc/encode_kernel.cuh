@@ -50,9 +50,11 @@ namespace qb
         EncResult*      results;     // [n_images]
         uint64_t*       desc;        // [n_images * tiles_per_image][kEncDescWords]
         uint32_t*       ticket;
-        uint32_t*       scratch;     // encode_ts_kernel: per-tile records between its encode and copy roles
-        uint32_t        lag;         // encode_ts_kernel: finished tiles between the two roles of a tile
-        uint32_t        ticket_base[2];  // encode_ts_kernel: values of ticket[0], ticket[1] at launch (never reset)
+        uint32_t*       scratch;     // encode_ts_kernel: per-tile records, read by encode_ts_copy_kernel
+        uint32_t*       tile_bytes;  // encode_ts_kernel: [tiles] byte count of every tile
+        uint32_t*       group_bytes; // encode_ts_kernel: [n_images][groups_per_image] totals of 64-tile groups (zeroed before launch)
+        uint32_t        groups_per_image;
+        uint32_t        ticket_base[1];  // encode_ts_kernel: value of *ticket at launch (never reset)
     };
 
     constexpr int kEncWarps = 8, kEncThreads = kEncWarps * 32;

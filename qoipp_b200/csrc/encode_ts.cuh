@@ -20,10 +20,13 @@
 //          differing pixel, run counter; chunks are appended through a 64-bit register window to the lane's
 //          word-aligned slice of the tile's SCRATCH record in global memory ([word][lane]: whole 128-byte lines);
 //          then the tile's byte count is published and the warp is done with the tile;
-//   copy   `lag` finished tiles later some warp turns that record into the final bytes: look back over the byte
-//          counts -- by then the predecessors have long published, nobody waits for a slow neighbour --, prefix-sum
-//          the 32 per-lane counts, funnel-shift the slices into one contiguous run in shared memory, realigned
-//          16-byte copy-out.
+//   copy   a second kernel (encode_ts_copy_kernel, one warp per tile) turns the records into the final bytes: the tile's
+//          offset is a sum of 64-tile group totals (accumulated by the encode kernel with one atomicAdd per tile) and of
+//          the byte counts of the earlier tiles of its group -- no chain, nothing to wait for --, then the 32 per-lane
+//          counts are prefix-summed, the slices funnel-shifted into one contiguous run in shared memory and copied out
+//          as realigned 16-byte stores.  Measured alternatives (profiles/r01_experiments.md): byte carry inside the encode
+//          pass (every tile synchronises to the slowest of its 32 predecessors), copy role inside the same kernel behind
+//          a ticket lag (the copying warps wait for stragglers half of their time).
 #pragma once
 
 #include "encode_kernel.cuh"
@@ -45,8 +48,13 @@ namespace qb
         static constexpr int kScrWords  = (kPrivWords + 1) * 32;    // scratch record of a tile: [word][lane], then the counts
     };
 
+    constexpr int kTsCopyWarps = 8;  // encode_ts_copy_kernel: tiles (warps) per CTA
+    struct TsCopySmem {
+        alignas(16) unsigned tab[(kTsT * 5 + 64) / 4];  // the tile's staging bytes
+    };
+
     struct TsWarpSmem {
-        alignas(16) unsigned tab[64 * kTsRow];  // [slot][lane]; in the copy role: the tile's staging bytes (<= 5120 + 48)
+        alignas(16) unsigned tab[64 * kTsRow];  // [slot][lane]
         unsigned gin[64];                       // table on entry to the tile
     };
 
@@ -203,21 +211,10 @@ namespace qb
         QB_STAMP(desc, 67, 0, qb_t0);  // merge
 
         // ================= look back: table on entry to the tile, run counter on entry =================
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const unsigned s = 32u * h + lane;
-            unsigned       e;
-            int            p = (int)t - 1;
-            for (;;) {
-                if (p < 0) { e = 0u; break; }  // simple.cpp:28: zero-initialised table
-                const uint64_t wd = wait_word(desc - (int64_t)(t - p) * kEncDescWords + s, epoch);
-                if (word_status(wd, epoch) == ST_AGG_EMPTY) { --p; continue; }
-                e = (unsigned)word_payload(wd);
-                break;
-            }
-            if (own[h] == sentinel(s)) st_word(desc + s, pack_word(e, ST_INCL, epoch));
-            sm.gin[s] = e;
-        }
+        // the first probes of all three look-backs are in flight together
+        const uint64_t* prev_rec = desc - kEncDescWords;
+        uint64_t        first_wd[2] = { 0, 0 };
+        if (t > 0) first_wd[0] = ld_word(prev_rec + lane), first_wd[1] = ld_word(prev_rec + 32 + lane);
         unsigned base62;
         {
             // payload = last differing pixel index + bias (never 0); the later tile wins when it has one
@@ -231,6 +228,29 @@ namespace qb
                 [](uint64_t a, uint64_t b) { return b ? b : a; });
             if (lane == 0 && !tile_last) st_word(desc + kWordLne, pack_word(lp, ST_INCL, epoch));
             base62 = (unsigned)((tile_start + kLneBias - lp) % kRunLimit);  // (tile_start - last differing) mod 62
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned s = 32u * h + lane;
+            unsigned       e;
+            int            p  = (int)t - 1;
+            uint64_t       wd = first_wd[h];
+            for (;;) {
+                if (p < 0) { e = 0u; break; }  // simple.cpp:28: zero-initialised table
+                const uint64_t* src = desc - (int64_t)(t - p) * kEncDescWords + s;
+                while (word_status(wd, epoch) == ST_NONE) {
+                    QB_SPIN_YIELD();
+                    wd = ld_word(src);
+                }
+                if (word_status(wd, epoch) == ST_AGG_EMPTY) {
+                    if (--p >= 0) wd = ld_word(src - kEncDescWords);
+                    continue;
+                }
+                e = (unsigned)word_payload(wd);
+                break;
+            }
+            if (own[h] == sentinel(s)) st_word(desc + s, pack_word(e, ST_INCL, epoch));
+            sm.gin[s] = e;
         }
         __syncwarp();
         QB_STAMP(desc, 67, 1, qb_t0);  // table / run look-back
@@ -283,22 +303,21 @@ namespace qb
         const unsigned total = nw * 4u + fill;
         QB_STAMP(desc, 68, 0, qb_t0);  // encode loop
 
-        // ================= carry (3): the tile's byte count; the record is complete =================
+        // ================= the tile's byte count =================
         priv[C::kPrivWords * 32] = total;
         unsigned tile_bytes = total;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) tile_bytes += __shfl_xor_sync(kFull, tile_bytes, d);
-        __syncwarp();  // every lane's scratch stores are ordered before lane 0's fence
         if (lane == 0) {
-            __threadfence();  // the record before the word that announces it
-            st_word(desc + kWordBytes, pack_word(tile_bytes, ST_AGG, epoch));
+            P.tile_bytes[gt] = tile_bytes;
+            atomicAdd(P.group_bytes + (uint64_t)img * P.groups_per_image + (t >> 6), tile_bytes);
         }
-        QB_STAMP(desc, 68, 1, qb_t0);  // publish
+        QB_STAMP(desc, 68, 1, qb_t0);  // counts
     }
 
     // ---- copy role: scratch record of tile `gt` -> the tile's bytes at their final place.  One warp.
     template <int CH>
-    __device__ __forceinline__ void ts_copy_tile(const EncParams& P, TsWarpSmem& sm, unsigned gt)
+    __device__ __forceinline__ void ts_copy_tile(const EncParams& P, TsCopySmem& sm, unsigned gt)
     {
         using C             = TsCfg<CH>;
         const unsigned lane = threadIdx.x & 31u;
@@ -306,29 +325,24 @@ namespace qb
         const unsigned  img     = gt / P.tiles_per_image;
         const unsigned  t       = gt % P.tiles_per_image;
         uint8_t*        out_img = P.out + (uint64_t)img * P.out_stride;
-        uint64_t*       desc    = P.desc + (uint64_t)gt * kEncDescWords;
-        const unsigned  epoch   = P.epoch;
+        [[maybe_unused]] uint64_t* desc = P.desc + (uint64_t)gt * kEncDescWords;
         const unsigned* priv    = P.scratch + (uint64_t)gt * C::kScrWords + lane;
 
-        // the encoder of this tile started before this warp took its copy ticket: it is running or done
-        unsigned tile_bytes = 0;
-        if (lane == 0) {
-            tile_bytes = (unsigned)word_payload(wait_word(desc + kWordBytes, epoch));
-            __threadfence();  // the word before the record it announces
+        // where the tile's bytes start: header + the totals of the earlier 64-tile groups + the earlier tiles of this group
+        const unsigned tile_bytes = P.tile_bytes[gt];
+        uint64_t       tile_off   = 0;
+        {
+            const uint32_t* gb = P.group_bytes + (uint64_t)img * P.groups_per_image;
+            const unsigned  g  = t >> 6;
+            for (unsigned i = lane; i < g; i += 32) tile_off += gb[i];
+            const unsigned j0 = gt - (t & 63u);  // first tile of the group
+            for (unsigned j = j0 + lane; j < gt; j += 32) tile_off += P.tile_bytes[j];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) tile_off += __shfl_xor_sync(kFull, tile_off, d);
+            tile_off += kHeader;
         }
-        tile_bytes = __shfl_sync(kFull, tile_bytes, 0);
-        // where the tile's bytes start: look back over the byte counts, 32 predecessors per round
-        const uint64_t tile_off = warp_lookback_lazy<uint64_t>(
-            t, (uint64_t)kHeader, (uint64_t)0,
-            [&](unsigned p, unsigned& st) {
-                const uint64_t wd = ld_word(desc - (int64_t)(t - p) * kEncDescWords + kWordBytes);
-                st                = word_status(wd, epoch);
-                return word_payload(wd);
-            },
-            [](uint64_t a, uint64_t b) { return a + b; });
-        if (lane == 0) st_word(desc + kWordBytes, pack_word(tile_off + tile_bytes, ST_INCL, epoch));
         // per-lane byte counts -> offsets inside the tile
-        const unsigned total = __ldcg(priv + C::kPrivWords * 32);
+        const unsigned total = priv[C::kPrivWords * 32];
         unsigned       off;
         {
             unsigned inc = total;
@@ -339,17 +353,33 @@ namespace qb
             }
             off = inc - total;
         }
-        QB_STAMP(desc, 69, 0, qb_t0);  // copy: record, look-back, counts
+        QB_STAMP(desc, 69, 0, qb_t0);  // copy: offsets
 
         // ================= compaction: the lanes' word-aligned slices -> the tile's contiguous bytes =================
         unsigned char* const stage = reinterpret_cast<unsigned char*>(sm.tab);
-        if (total) {
+        {
             // destination word m (from the word holding my first byte) = my bytes 4m - a .. 4m - a + 3: slice words m - 1 and m
-            // funnel-shifted; only the first and the last destination word can be shared with a neighbour (byte stores)
+            // funnel-shifted; only the first and the last destination word can be shared with a neighbour (byte stores).
+            // All slice words are loaded up front (one round trip), the rest runs out of registers.
+            constexpr int  PW = C::kPrivWords;
             const unsigned a = off & 3u, rs = 32u - a * 8u;
             unsigned*      d32 = reinterpret_cast<unsigned*>(stage) + (off >> 2);
             const unsigned nwp = (total + 3u) >> 2;      // slice words holding bytes
-            const unsigned nd  = (total + a + 3u) >> 2;  // destination words touched
+            const unsigned nd  = (total + a + 3u) >> 2;  // destination words touched (<= PW)
+            unsigned       hw[PW];
+#pragma unroll
+            for (int i = 0; i < PW; ++i) hw[i] = (unsigned)i < nwp ? priv[i * 32] : 0u;
+            unsigned v_first = 0, v_last = 0;
+#pragma unroll
+            for (int m = 0; m < PW; ++m) {
+                const unsigned v = __funnelshift_rc(m ? hw[m ? m - 1 : 0] : 0u, hw[m], rs);
+                if ((unsigned)m < nd) {
+                    const bool whole = (m > 0 || a == 0) && 4u * m + 4u <= total + a;
+                    if (whole) d32[m] = v;
+                    else if (m == 0) v_first = v;
+                    else v_last = v;
+                }
+            }
             auto partial = [&](unsigned m, unsigned v) {
                 const unsigned b0 = m == 0 ? a : 0u, b1 = min(4u, total + a - 4u * m);
                 unsigned char* d = reinterpret_cast<unsigned char*>(d32 + m);
@@ -357,29 +387,9 @@ namespace qb
                 for (unsigned bb = 0; bb < 4; ++bb)
                     if (bb >= b0 && bb < b1) d[bb] = (unsigned char)(v >> (8u * bb));
             };
-            unsigned lo = __ldcg(priv);
-            {
-                const unsigned v = __funnelshift_rc(0u, lo, rs);
-                if (a == 0 && total >= 4u) d32[0] = v;
-                else partial(0u, v);
-            }
-            unsigned m = 1;
-            for (; m + 8u < nd; m += 8u) {  // eight whole words per round, loads first
-                unsigned h[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) h[i] = __ldcg(priv + (m + i) * 32);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    d32[m + i] = __funnelshift_rc(lo, h[i], rs);
-                    lo         = h[i];
-                }
-            }
-            for (; m < nd; ++m) {
-                const unsigned hi = m < nwp ? __ldcg(priv + m * 32) : 0u;
-                const unsigned v  = __funnelshift_rc(lo, hi, rs);
-                lo                = hi;
-                if (m + 1u < nd || ((total + a) & 3u) == 0) d32[m] = v;
-                else partial(m, v);
+            if (total) {
+                if (!(a == 0 && total >= 4u)) partial(0u, v_first);
+                if (nd > 1 && ((total + a) & 3u) != 0) partial(nd - 1u, v_last);
             }
         }
         __syncwarp();
@@ -413,33 +423,34 @@ namespace qb
             res->complete  = 1;
             res->processed = P.n_pixels;
         }
-        __syncwarp();  // the staging bytes are read: the next encode role may reuse the memory
         QB_STAMP(desc, 70, 0, qb_t0);  // copy: copy-out
     }
 
-    // Persistent, independent warps.  A warp draws ticket x (handed out in start order; the counters never reset, the host
-    // passes their values at launch): it encodes tile x (x < tiles), then draws a copy ticket c (handed out in FINISHING
-    // order) and copies tile c - lag: at least c warps finished an encode role before, so that tile's encoder started long
-    // ago and, `lag` finishers later, is done in practice; the copy role therefore finds every word it looks back on already
-    // published, and no tile waits for a slow neighbour.  Every tile a running warp can wait for has a running (or finished)
-    // encoder, because tickets are issued in order, so the waits cannot deadlock.  Tickets >= tiles only drain copies.
+    // Encode kernel: persistent, independent warps draw tiles from a ticket counter in start order, so every tile a running
+    // warp waits for (table / run look-back) is held by a warp that is running too or done.  The counter never resets: the
+    // host passes its value at launch, every warp draws exactly one ticket beyond the last tile.
     template <int CH>
     __global__ void __launch_bounds__(kTsThreads, QB_TS_CTAS) encode_ts_kernel(const EncParams P)
     {
         TsWarpSmem&    sm      = reinterpret_cast<TsWarpSmem*>(QB_DYN_SMEM)[threadIdx.x >> 5];
         const unsigned lane    = threadIdx.x & 31u;
-        const unsigned n_tiles = P.tiles_per_image * P.n_images, n_tickets = n_tiles + P.lag;
+        const unsigned n_tiles = P.tiles_per_image * P.n_images;
         for (;;) {
             unsigned x = 0;
             if (lane == 0) x = atomicAdd(P.ticket, 1u) - P.ticket_base[0];
             x = __shfl_sync(kFull, x, 0);
-            if (x >= n_tickets) break;
-            if (x < n_tiles) ts_encode_tile<CH>(P, sm, x);
-            __syncwarp();  // the table's memory becomes the staging bytes
-            unsigned c = 0;
-            if (lane == 0) c = atomicAdd(P.ticket + 1, 1u) - P.ticket_base[1];
-            c = __shfl_sync(kFull, c, 0);
-            if (c >= P.lag) ts_copy_tile<CH>(P, sm, c - P.lag);
+            if (x >= n_tiles) break;
+            ts_encode_tile<CH>(P, sm, x);
+            __syncwarp();
         }
+    }
+
+    // Copy kernel: one warp per tile, launched behind the encode kernel on the same stream.
+    template <int CH>
+    __global__ void __launch_bounds__(kTsCopyWarps * 32) encode_ts_copy_kernel(const EncParams P)
+    {
+        TsCopySmem&    sm = reinterpret_cast<TsCopySmem*>(QB_DYN_SMEM)[threadIdx.x >> 5];
+        const unsigned gt = blockIdx.x * kTsCopyWarps + (threadIdx.x >> 5);
+        if (gt < P.tiles_per_image * P.n_images) ts_copy_tile<CH>(P, sm, gt);
     }
 }  // namespace qb

@@ -97,15 +97,15 @@ struct qoipp_b200_ctx {
     DevBuf   state;       // EncState / DecState carry-in for the resumable calls
     DevBuf   aux;         // decode: per-image offsets and first-tile ids of a batch
     DevBuf   fix;         // decode: per-tile lists of alphas learned by the retry rounds
-    DevBuf   scratch;     // encode_ts_kernel: per-tile records between the encode and copy roles
+    DevBuf   scratch;     // encode_ts_kernel: per-tile records, read by encode_ts_copy_kernel
+    DevBuf   counts;      // encode_ts_kernel: byte counts per tile and per 64-tile group
     DevBuf   stage_in, stage_out;  // device staging of the host-pointer calls
     PinnedBuf h_result;   // pinned landing zone for result structs
     PinnedBuf h_pin_in, h_pin_out;
     cudaStream_t own_stream = nullptr;
     bool     enc_trivial = false;  // last encode needed no launch (capacity below the header)
     bool     attrs_set   = false;
-    uint32_t ts_ticket[2] = { 0, 0 };  // encode_ts_kernel: current values of its two ticket counters
-    uint32_t ts_lag = 512;
+    uint32_t ts_ticket = 0;  // encode_ts_kernel: current value of its ticket counter
     bool     force_general = false;  // QOIPP_B200_GENERAL=1: always the general kernels (A/B measurements, tests)
     int      dec_coresident = 148;  // CTAs of decode_finish_kernel that fit on the device at once
 
@@ -152,6 +152,8 @@ namespace
         if ((e = allow_smem(encode_kernel<4, kEncK>, sizeof(EncSmem<kEncK>))) != cudaSuccess) return e;
         if ((e = allow_smem(encode_ts_kernel<3>, kTsWarps * sizeof(TsWarpSmem))) != cudaSuccess) return e;
         if ((e = allow_smem(encode_ts_kernel<4>, kTsWarps * sizeof(TsWarpSmem))) != cudaSuccess) return e;
+        if ((e = allow_smem(encode_ts_copy_kernel<3>, kTsCopyWarps * sizeof(TsCopySmem))) != cudaSuccess) return e;
+        if ((e = allow_smem(encode_ts_copy_kernel<4>, kTsCopyWarps * sizeof(TsCopySmem))) != cudaSuccess) return e;
         if ((e = dec_set_attrs()) != cudaSuccess) return e;
         int per_sm = 0;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_finish_kernel, kDecThreads, sizeof(DecSmem))) != cudaSuccess) return e;
@@ -205,20 +207,30 @@ namespace
         if (ts) {
             const uint64_t n_tiles   = tiles * n_images;
             const uint64_t scr_words = ch == 3 ? TsCfg<3>::kScrWords : TsCfg<4>::kScrWords;
-            if (n_tiles * scr_words * 4 > c->scratch.cap) QB_CUDA(cudaStreamSynchronize(s));  // an earlier launch may still use it
+            const uint64_t groups    = (tiles + 63) / 64;
+            if (n_tiles * scr_words * 4 > c->scratch.cap || (n_tiles + groups * n_images) * 4 > c->counts.cap)
+                QB_CUDA(cudaStreamSynchronize(s));  // an earlier launch may still use the buffers
             QB_CUDA(c->scratch.reserve(n_tiles * scr_words * 4));
-            P.scratch = static_cast<uint32_t*>(c->scratch.p);
-            P.lag     = (uint32_t)std::min<uint64_t>(n_tiles, c->ts_lag);  // see encode_ts_kernel
-            // persistent warps: one CTA slot per resident CTA; the ticket counters are never reset, every warp draws exactly
-            // one ticket beyond the last valid one
-            const uint64_t n_tickets = n_tiles + P.lag;
-            const unsigned n_ctas    = (unsigned)std::min<uint64_t>((n_tickets + kTsWarps - 1) / kTsWarps, (uint64_t)c->sm_count * QB_TS_CTAS);
+            QB_CUDA(c->counts.reserve((n_tiles + groups * n_images) * 4));
+            P.scratch          = static_cast<uint32_t*>(c->scratch.p);
+            P.tile_bytes       = static_cast<uint32_t*>(c->counts.p);
+            P.group_bytes      = P.tile_bytes + n_tiles;
+            P.groups_per_image = (uint32_t)groups;
+            QB_CUDA(cudaMemsetAsync(P.group_bytes, 0, groups * n_images * 4, s));
+            // persistent warps: one CTA per resident slot; the ticket counter is never reset, every warp draws exactly one
+            // ticket beyond the last tile
+            const unsigned n_ctas = (unsigned)std::min<uint64_t>((n_tiles + kTsWarps - 1) / kTsWarps, (uint64_t)c->sm_count * QB_TS_CTAS);
             P.ticket         = static_cast<uint32_t*>(c->tickets.p) + 8;
-            P.ticket_base[0] = c->ts_ticket[0], P.ticket_base[1] = c->ts_ticket[1];
-            c->ts_ticket[0] += (uint32_t)n_tickets + n_ctas * kTsWarps;
-            c->ts_ticket[1] += (uint32_t)n_tickets;
-            if (ch == 3) encode_ts_kernel<3><<<dim3(n_ctas), dim3(kTsThreads), kTsWarps * sizeof(TsWarpSmem), s>>>(P);
-            else encode_ts_kernel<4><<<dim3(n_ctas), dim3(kTsThreads), kTsWarps * sizeof(TsWarpSmem), s>>>(P);
+            P.ticket_base[0] = c->ts_ticket;
+            c->ts_ticket += (uint32_t)n_tiles + n_ctas * kTsWarps;
+            const dim3 grid2((unsigned)((n_tiles + kTsCopyWarps - 1) / kTsCopyWarps)), block2(kTsCopyWarps * 32);
+            if (ch == 3) {
+                encode_ts_kernel<3><<<dim3(n_ctas), dim3(kTsThreads), kTsWarps * sizeof(TsWarpSmem), s>>>(P);
+                encode_ts_copy_kernel<3><<<grid2, block2, kTsCopyWarps * sizeof(TsCopySmem), s>>>(P);
+            } else {
+                encode_ts_kernel<4><<<dim3(n_ctas), dim3(kTsThreads), kTsWarps * sizeof(TsWarpSmem), s>>>(P);
+                encode_ts_copy_kernel<4><<<grid2, block2, kTsCopyWarps * sizeof(TsCopySmem), s>>>(P);
+            }
         } else {
             if (ch == 3) encode_kernel<3, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
             else encode_kernel<4, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
@@ -290,7 +302,6 @@ extern "C"
         }
         c->sm_count = prop.multiProcessorCount;
         if (const char* g = std::getenv("QOIPP_B200_GENERAL")) c->force_general = g[0] == '1';
-        if (const char* g = std::getenv("QOIPP_B200_TS_LAG")) c->ts_lag = (uint32_t)std::max(1, std::atoi(g));  // development knob
         *out        = c;
         return 0;
     }
@@ -300,7 +311,7 @@ extern "C"
         if (!c) return 0;
         Guard g(c->device);
         cudaDeviceSynchronize();
-        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release(), c->scratch.release();
+        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release(), c->scratch.release(), c->counts.release();
         c->stage_in.release(), c->stage_out.release();
         c->h_result.release(), c->h_pin_in.release(), c->h_pin_out.release();
         if (c->own_stream) cudaStreamDestroy(c->own_stream);

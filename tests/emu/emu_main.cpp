@@ -26,14 +26,15 @@ namespace
     void run_encode_ts(const EncParams& P, int resident, uint64_t seed)
     {
         EncParams Q = P;
-        const unsigned n_tiles = P.tiles_per_image * P.n_images;
-        std::vector<uint32_t> scratch((size_t)n_tiles * TsCfg<CH>::kScrWords, 0xDEADBEEFu);
-        uint32_t tickets[2] = { 1000u + (uint32_t)seed, 0xFFFFFFF0u };  // the counters never reset (and may wrap)
-        Q.scratch = scratch.data();
-        Q.lag     = std::min<unsigned>(n_tiles, (unsigned)(seed % 3 + 1));  // small lags: the copy role does have to wait here
-        Q.ticket = tickets; Q.ticket_base[0] = tickets[0]; Q.ticket_base[1] = tickets[1];
-        const unsigned n_ctas = std::min<unsigned>((n_tiles + Q.lag + kTsWarps - 1) / kTsWarps, (unsigned)resident);
+        const unsigned n_tiles = P.tiles_per_image * P.n_images, groups = (P.tiles_per_image + 63) / 64;
+        std::vector<uint32_t> scratch((size_t)n_tiles * TsCfg<CH>::kScrWords, 0xDEADBEEFu), counts(n_tiles + (size_t)groups * P.n_images, 0);
+        uint32_t ticket = 0xFFFFFFF0u + (uint32_t)seed;  // the counter never resets (and may wrap)
+        Q.scratch = scratch.data(); Q.tile_bytes = counts.data(); Q.group_bytes = counts.data() + n_tiles; Q.groups_per_image = groups;
+        Q.ticket = &ticket; Q.ticket_base[0] = ticket;
+        const unsigned n_ctas = std::min<unsigned>((n_tiles + kTsWarps - 1) / kTsWarps, (unsigned)resident);
         emu::launch(dim3(n_ctas), dim3(kTsThreads), kTsWarps * sizeof(TsWarpSmem) + 128, [=] { encode_ts_kernel<CH>(Q); }, resident, seed);
+        emu::launch(dim3((n_tiles + kTsCopyWarps - 1) / kTsCopyWarps), dim3(kTsCopyWarps * 32), kTsCopyWarps * sizeof(TsCopySmem) + 128,
+                    [=] { encode_ts_copy_kernel<CH>(Q); }, resident, seed);
     }
 
     // K == kTsK selects the thread-serial kernel (encode_ts.cuh), any other K the general kernel with K pixels per lane

@@ -110,3 +110,16 @@ def test_batch_images_share_one_launch():
     for raw, (out, n, ok) in zip(imgs, res):
         ref = Oracle.encode(raw, w, h, ch)
         assert ok and n == ref.size and np.array_equal(out[:n], ref)
+
+
+def test_more_than_one_tile_group():
+    # tile offsets are sums of 64-tile group totals plus the earlier tiles of the group: 2.x groups per image here
+    for ch, kind in ((3, "photo"), (4, "dither")):
+        w, h = 410, 333  # 136530 pixels: 134 tiles
+        check(synth.generate(kind, w, h, ch), w, h, ch, seed=3, resident=3)
+    w, h, ch = 272, 256, 4  # 69632 pixels: exactly 68 tiles, raw stride 16-byte aligned
+    imgs = [synth.generate("photo", w, h, ch, seed=7 + k) for k in range(2)]
+    res = E.encode(aligned(np.concatenate(imgs)), w, h, ch, K=TS, n_images=2, seed=4)
+    for raw, (out, n, ok) in zip(imgs, res):
+        ref = Oracle.encode(raw, w, h, ch)
+        assert ok and n == ref.size and np.array_equal(out[:n], ref)

@@ -8,7 +8,7 @@ from qoipp_b200._lib import Desc
 L = C.CDLL("qoipp_b200/libqoipp_b200_timing.so")
 ctx = C.c_void_p(); assert L.qoipp_b200_ctx_create(0, C.byref(ctx)) == 0
 st = torch.cuda.current_stream().cuda_stream
-names = ["loads", "W1", "merge", "lookback table/run", "encode loop", "publish"]
+names = ["loads", "W1", "merge", "lookback table/run", "encode loop", "counts"]
 T = 1024
 for kind, w, h, ch in [("photo", 3840, 2160, 3), ("photo", 7680, 4320, 4)]:
     raw = synth.generate(kind, w, h, 3)
@@ -33,5 +33,5 @@ for kind, w, h, ch in [("photo", 3840, 2160, 3), ("photo", 7680, 4320, 4)]:
         print(f"   {nm:20s} median {np.median(d[:, i]):8.0f}  p10 {np.percentile(d[:, i], 10):8.0f}  p90 {np.percentile(d[:, i], 90):8.0f}")
     c = words[:, 138:141].astype(np.int64)
     c = c[(c[:, -1] > 0) & (c[:, -1] < 10**7)]
-    for i, nm in enumerate(["copy: record+lookback", "copy: compaction", "copy: copy-out"]):
+    for i, nm in enumerate(["copy: offsets", "copy: compaction", "copy: copy-out"]):
         print(f"   {nm:22s} median {np.median(c[:, i]):8.0f}  p90 {np.percentile(c[:, i], 90):8.0f}   (cumulative)")
