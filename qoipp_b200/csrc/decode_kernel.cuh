@@ -45,13 +45,15 @@ namespace qb
         uint64_t processed;  // resumable decode: input bytes consumed / output bytes written / carry-out
         uint64_t written;
         uint32_t first_bad[kDecRounds + 1];  // per round: 0 = all verified, else 0xFFFFFFFF - first refuted tile
-        uint32_t pad[3];
+        uint32_t pad[3];  // pad[0]: decode_ts_kernel (the fast path) was refuted for this image, decode it with decode_tile
         DecState state;
     };
 
     struct DecControl {  // zeroed with the results before every decode
         uint32_t tickets[kDecRounds + 1];  // tile tickets of the retry rounds
         uint32_t any_bad[kDecRounds + 1];  // some image needs round r + 1
+        uint32_t fast_any_bad;             // decode_ts_kernel was refuted for some image
+        uint32_t ticket0;                  // tile tickets of the round-0 pass over those images
     };
 
     struct DecParams {
@@ -69,6 +71,7 @@ namespace qb
         uint64_t*       desc;
         uint32_t*       fix;  // [n_tiles][kFixWords]: alpha learned at OP_RGB ops by earlier rounds
         uint32_t*       ticket;
+        uint32_t        fast_used;  // round 0 was decode_ts_kernel: decode_finish_kernel decodes the images it flagged
     };
 
     constexpr int kFixWords = 32, kFixMax = kFixWords - 1;  // word 0: count | decode tag << 8; entries: pos | alpha << 16
@@ -381,11 +384,11 @@ namespace qb
         const Map excl_map = cta_exclusive_scan(mymap, sm.wmap, map_identity(), [](const Map& a, const Map& b) { return map_compose(a, b); }, tile_map);
         if (w == 0) {  // 32 predecessors per look-back round; an inclusive word is the constant map "exit offset"
             if (lane == 0 && t > 0) st_word(desc + kDwParse, pack_word(map_pack(tile_map), ST_AGG, epoch));
-            const Map in = warp_lookback<Map>(
+            const Map in = warp_lookback_lazy<Map>(
                 t, map_const(0), map_identity(),
                 [&](unsigned p, unsigned& st) {
-                    const uint64_t wd = wait_word(word_of(p, kDwParse), ep, p);
-                    st                = raw_status(wd);
+                    const uint64_t wd = ld_word(word_of(p, kDwParse));
+                    st                = ep.valid(wd, p) ? raw_status(wd) : (unsigned)ST_NONE;
                     return map_unpack((unsigned)word_payload(wd));
                 },
                 [](const Map& a, const Map& b) { return map_compose(a, b); });
@@ -433,11 +436,11 @@ namespace qb
         if (w == 0) {  // pixels before this tile
             const unsigned npix = tot.cnt & 0xFFFFFu;
             if (lane == 0 && t > 0) st_word(desc + kDwPix, pack_word(npix, ST_AGG, epoch));
-            const uint64_t base = warp_lookback<uint64_t>(
+            const uint64_t base = warp_lookback_lazy<uint64_t>(
                 t, (uint64_t)0, (uint64_t)0,
                 [&](unsigned p, unsigned& st) {
-                    const uint64_t wd = wait_word(word_of(p, kDwPix), ep, p);
-                    st                = raw_status(wd);
+                    const uint64_t wd = ld_word(word_of(p, kDwPix));
+                    st                = ep.valid(wd, p) ? raw_status(wd) : (unsigned)ST_NONE;
                     return word_payload(wd);
                 },
                 [](uint64_t a, uint64_t b) { return a + b; });
@@ -458,16 +461,17 @@ namespace qb
             };
             const Seg start = Seg{ 0u, 255u << 24, 53u << 16 | kFlRoot | kFlRgba };  // {0,0,0,255}: slot 53 (simple.cpp:108)
             if (lane == 0 && t > 0) st_word(desc + kDwSlot, pack_word(pack(tot), ST_AGG, epoch));
-            const Seg acc = warp_lookback<Seg>(
+            const Seg acc = warp_lookback_lazy<Seg>(
                 t, start, seg_identity(),
                 [&](unsigned p, unsigned& st) {
                     if (p < ep.fresh_from) {  // a tile finished by an earlier round: take slot and alpha of its actual last pixel
-                        const unsigned v = (unsigned)word_payload(wait_word(word_of(p, kDwState + 64), ep, p));
-                        st               = ST_INCL;
+                        const uint64_t wd = ld_word(word_of(p, kDwState + 64));
+                        const unsigned v  = (unsigned)word_payload(wd);
+                        st                = ep.valid(wd, p) ? (unsigned)ST_INCL : (unsigned)ST_NONE;
                         return Seg{ 0u, v & 0xFF000000u, slot_of(v) << 16 | kFlRoot | kFlRgba };
                     }
-                    const uint64_t wd = wait_word(word_of(p, kDwSlot), ep, p);
-                    st                = raw_status(wd);
+                    const uint64_t wd = ld_word(word_of(p, kDwSlot));
+                    st                = ep.valid(wd, p) ? raw_status(wd) : (unsigned)ST_NONE;
                     return unpack(word_payload(wd));
                 },
                 [](const Seg& a, const Seg& b) { return combine(a, b); });
@@ -942,6 +946,22 @@ namespace qb
     __global__ void __launch_bounds__(kDecThreads, 5) decode_finish_kernel(const DecParams P)
     {
         DecSmem& sm = *reinterpret_cast<DecSmem*>(QB_DYN_SMEM);
+        if (P.fast_used && P.control->fast_any_bad) {  // same value in every CTA: final when this kernel starts
+            // round 0 of the general path for the images the thread-serial fast path (decode_ts.cuh) could not verify
+            for (;;) {
+                __syncthreads();
+                if (threadIdx.x == 0) sm.ticket = atomicAdd(&P.control->ticket0, 1u);
+                __syncthreads();
+                if (sm.ticket >= P.n_tiles) break;
+                unsigned       img, t, ntiles;
+                const uint8_t* stream;
+                uint64_t       size;
+                locate_image(P, sm.ticket, img, t, ntiles, stream, size);
+                if (P.results[img].pad[0] == 0) continue;
+                decode_tile(P, sm, 0u, img, t, ntiles, stream, size, 0u);
+            }
+            QB_GRID_SYNC();
+        }
         for (unsigned round = 1; round <= (unsigned)kDecRounds; ++round) {
             if (P.control->any_bad[round - 1] == 0) break;  // same value in every CTA: final since the last barrier
             for (;;) {

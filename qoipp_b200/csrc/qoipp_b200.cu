@@ -4,6 +4,7 @@
 #include "../../include/qoipp_b200.h"
 
 #include "decode_kernel.cuh"
+#include "decode_ts.cuh"
 #include "encode_kernel.cuh"
 #include "encode_ts.cuh"
 #include "host_util.hpp"
@@ -106,6 +107,7 @@ struct qoipp_b200_ctx {
     bool     enc_trivial = false;  // last encode needed no launch (capacity below the header)
     bool     attrs_set   = false;
     uint32_t ts_ticket = 0;  // encode_ts_kernel: current value of its ticket counter
+    uint32_t dt_ticket = 0;  // decode_ts_kernel: likewise
     bool     force_general = false;  // QOIPP_B200_GENERAL=1: always the general kernels (A/B measurements, tests)
     int      dec_coresident = 148;  // CTAs of decode_finish_kernel that fit on the device at once
 
@@ -155,6 +157,7 @@ namespace
         if ((e = allow_smem(encode_ts_copy_kernel<3>, kTsCopyWarps * sizeof(TsCopySmem))) != cudaSuccess) return e;
         if ((e = allow_smem(encode_ts_copy_kernel<4>, kTsCopyWarps * sizeof(TsCopySmem))) != cudaSuccess) return e;
         if ((e = dec_set_attrs()) != cudaSuccess) return e;
+        if ((e = allow_smem(decode_ts_kernel, kDtWarps * sizeof(DtWarpSmem))) != cudaSuccess) return e;
         int per_sm = 0;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_finish_kernel, kDecThreads, sizeof(DecSmem))) != cudaSuccess) return e;
         c->dec_coresident = std::max(1, per_sm) * c->sm_count;
