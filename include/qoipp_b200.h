@@ -92,7 +92,8 @@ int32_t qoipp_b200_stream_encode_host(qoipp_b200_ctx* ctx, qoipp_b200_state* sta
 int32_t qoipp_b200_decode_dev(qoipp_b200_ctx* ctx, const uint8_t* d_qoi, uint64_t qoi_size, const qoipp_b200_desc* desc,
                               uint8_t target_channels, int32_t flip_vertically, uint8_t* d_out, uint64_t out_cap,
                               void* stream);
-/* 0 when the last decode on this context completed; *path: 0 = parallel path, 1 = exact serial re-decode */
+/* 0 when the last decode on this context completed; *path: 0 = verified in round 0, 1..4 = retry rounds used,
+ * + 100 = the sequential loop produced part of the image, + 1000 = the thread-serial fast path was refuted first */
 int32_t qoipp_b200_decode_status(qoipp_b200_ctx* ctx, void* stream, int32_t* path);
 
 int32_t qoipp_b200_decode_host(qoipp_b200_ctx* ctx, const uint8_t* h_qoi, uint64_t qoi_size, uint8_t target_channels,

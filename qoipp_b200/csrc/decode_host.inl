@@ -50,11 +50,14 @@ namespace
         return 0;
     }
 
-    // The fast path walks every lane's 68 stream bytes serially, long runs included: streams that are mostly OP_RUN (less
-    // than a quarter byte per pixel) stay on the general kernel, whose run expansion is cooperative.
+    // decode_ts_kernel (decode_ts.cuh) is opt-in (QOIPP_B200_DECODE_TS=1): exact and verified, but measured SLOWER than the
+    // general kernel in round 1 (4K RGB photo 321-407 us against 278 us: 18.6 KB of shared memory per warp leave 12 warps per
+    // SM, and three serial op walks cost as many instructions as the general kernel's phases; profiles/r01_experiments.md).
+    // It walks every lane's 68 stream bytes serially, long runs included, so streams that are mostly OP_RUN (less than a
+    // quarter byte per pixel) stay on the general kernel in any case.
     bool use_fast_decode(const qoipp_b200_ctx* c, uint64_t stream_bytes, uint64_t pixels, bool flip)
     {
-        return !c->force_general && !flip && stream_bytes * 4 >= pixels;
+        return c->decode_ts && !c->force_general && !flip && stream_bytes * 4 >= pixels;
     }
 }
 
@@ -89,9 +92,9 @@ extern "C"
         Guard g(c->device);
         auto  s = static_cast<cudaStream_t>(stream);
         auto* h = static_cast<DecResult*>(c->h_result.p);
-        QB_CUDA(cudaMemcpyAsync(h, static_cast<uint8_t*>(c->results.p) + kCtrlBytes, 16, cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaMemcpyAsync(h, static_cast<uint8_t*>(c->results.p) + kCtrlBytes, 64, cudaMemcpyDeviceToHost, s));
         QB_CUDA(cudaStreamSynchronize(s));
-        if (path) *path = (int32_t)h->path;
+        if (path) *path = (int32_t)h->path + (h->pad[0] ? 1000 : 0);
         return 0;
     }
 

@@ -98,19 +98,44 @@ namespace qb
         stream = D.qoi + o0, size = __ldg(D.offsets + lo + 1) - o0;
     }
 
-    // ops whose tag lies in chunk bytes [entry, end): f(p, tag, pay) with pay = the four bytes behind the tag
-    template <class F>
-    __device__ __forceinline__ void dt_walk(const unsigned* words, unsigned byte0, unsigned entry, unsigned end, F&& f)
+    // One op as the walks see it; everything is computed without branches (the lanes of a warp hold different kinds).
+    struct DtOp {
+        unsigned tag, pay;  // pay = the four bytes behind the tag
+        bool     rgb, rgba, index, run, delta;
+    };
+    __device__ __forceinline__ DtOp dt_op(unsigned lo, unsigned b4)
     {
-        unsigned p = entry;
-        while (p < end) {
+        DtOp o;
+        o.tag = lo & 0xFFu, o.pay = __funnelshift_r(lo, b4, 8);
+        const unsigned k = o.tag >> 6;
+        o.rgb = o.tag == kOpRgb, o.rgba = o.tag == kOpRgba;
+        o.index = k == 0, o.run = k == 3 && o.tag < kOpRgb, o.delta = k == 1 || k == 2;
+        return o;
+    }
+
+    // Ops of a lane's chunk in stream order.  `mlo` / `mhi` mark the chunk bytes (0..63 / 64..67) where an op starts (the
+    // parse already knows them), so the next op's position never waits for the current op: its bytes are fetched from shared
+    // memory one op ahead.
+    template <class F>
+    __device__ __forceinline__ void dt_walk(const unsigned* words, unsigned byte0, unsigned long long mlo, unsigned mhi, F&& f)
+    {
+        auto take = [&](unsigned& lo, unsigned& b4) {
+            unsigned p;
+            if (mlo) p = (unsigned)__ffsll((long long)mlo) - 1u, mlo &= mlo - 1ull;
+            else p = 63u + (unsigned)__ffs((int)mhi), mhi &= mhi - 1u;
             const unsigned  a  = byte0 + p, sh = (a & 3u) * 8u;
             const unsigned* w  = words + (a >> 2);
-            const unsigned  w0 = w[0], w1 = w[1], w2 = w[2];
-            const unsigned  lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-            const unsigned  tag = lo & 0xFFu;
-            f(p, tag, __funnelshift_r(lo, hi, 8));
-            p += op_length(tag);
+            const unsigned  w0 = w[0], w1 = w[1];
+            lo = __funnelshift_r(w0, w1, sh), b4 = w1 >> sh;
+        };
+        bool     more = (mlo | mhi) != 0;
+        unsigned lo = 0, b4 = 0;
+        if (more) take(lo, b4);
+        while (more) {
+            const unsigned clo = lo, cb4 = b4;
+            more = (mlo | mhi) != 0;
+            if (more) take(lo, b4);
+            f(dt_op(clo, cb4));
         }
     }
 
@@ -166,9 +191,9 @@ namespace qb
 
         QB_STAMP(desc, 68, 0, qb_t0);  // staged
         // ================= parse: entry offset of every lane =================
-        Map mymap;
+        Map      mymap;
+        unsigned bw[kDtSB / 4 + 1];  // chunk bytes 4j .. 4j+3
         {
-            unsigned        bw[kDtSB / 4 + 1];  // chunk bytes 4j .. 4j+3
             const unsigned* w  = words + (byte0 >> 2);
             const unsigned  sh = (byte0 & 3u) * 8u;
             unsigned        pw = w[0];
@@ -212,29 +237,42 @@ namespace qb
             if (lane == 0) st_word(desc + kDwParse, pack_word(map_pack(map_const(map_at(tile_map, entry))), ST_INCL, epoch));
             my_entry = map_at(excl, entry);
         }
+        // where the ops of this chunk start: forward over the bytes, `pend` = starts at byte j, j+1, .. j+4
+        unsigned long long mlo = 0;
+        unsigned           mhi = 0;
+        {
+            unsigned pend = 1u << my_entry;
+#pragma unroll
+            for (int j = 0; j < kDtSB; ++j) {
+                const unsigned cur = pend & 1u;
+                const unsigned L   = op_length((bw[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+                pend               = (pend >> 1) | (cur << (L - 1u));
+                if (j < 64) mlo |= (unsigned long long)cur << j;
+                else mhi |= cur << (j - 64);
+            }
+            // only tags below the end of the stream are ops
+            mlo = cend >= 64u ? mlo : mlo & ((1ull << cend) - 1ull);
+            mhi = cend >= 64u ? mhi & ((1u << (cend - 64u)) - 1u) : 0u;
+        }
 
         QB_STAMP(desc, 68, 1, qb_t0);  // parse + look-back
         // ================= W1: counts, slot / alpha carry =================
         Seg mine = seg_identity();
         {
             unsigned cnt = 0, delta = 0, c = 0, flags = 0, alpha = 0;
-            dt_walk(words, byte0, my_entry, cend, [&](unsigned p, unsigned tag, unsigned pay) {
-                (void)p;
-                if (tag == kOpRgb) {  // slot needs the inherited alpha: known if an OP_RGBA came earlier in this chunk
-                    const unsigned lin = __dp4a(pay & 0xFFFFFFu, 0x00070503u, 0u) & 63u;
-                    delta = 0, cnt += 1u | 1u << 20;
-                    if (flags & kFlRgba) c = lin + 11u * alpha, flags = kFlRoot | kFlRgba;
-                    else c = lin, flags = kFlRoot | kFlUses;
-                } else if (tag == kOpRgba) {
-                    delta = 0, c = slot_of(pay), alpha = pay >> 24, flags = kFlRoot | kFlRgba, cnt += 1u | 1u << 20;
-                } else if ((tag >> 6) == 0) {
-                    delta = 0, c = tag & 63u, flags = kFlRoot | (flags & kFlRgba), cnt += 1u | 1u << 20;
-                } else if ((tag >> 6) == 3) {
-                    cnt += ((tag & 63u) + 1u) | 1u << 20;  // OP_RUN
-                } else {
-                    const unsigned d = (tag >> 6) == 1 ? dt_diff_delta(tag) : dt_luma_delta(tag, pay);
-                    delta = add4(delta, d), c += dt_lin(d), cnt += 1u | 1u << 20;
-                }
+            dt_walk(words, byte0, mlo, mhi, [&](const DtOp& o) {
+                const unsigned d    = (o.tag >> 6) == 1 ? dt_diff_delta(o.tag) : dt_luma_delta(o.tag, o.pay);
+                const bool     seen = (flags & kFlRgba) != 0;  // an OP_RGBA came earlier in this chunk: its alpha is the OP_RGB's
+                const unsigned lin3 = __dp4a(o.pay & 0xFFFFFFu, 0x00070503u, 0u);
+                cnt += (o.run ? (o.tag & 63u) + 1u : 1u) | 1u << 20;
+                const bool root = o.rgb || o.rgba || o.index;
+                const unsigned c_root = o.rgb ? lin3 + (seen ? 11u * alpha : 0u) : (o.rgba ? slot_of(o.pay) : o.tag & 63u);
+                const unsigned f_root = o.rgb ? (seen ? kFlRoot | kFlRgba : kFlRoot | kFlUses)
+                                              : (o.rgba ? kFlRoot | kFlRgba : kFlRoot | (flags & kFlRgba));
+                delta = root ? 0u : (o.delta ? add4(delta, d) : delta);
+                c     = root ? c_root : (o.delta ? c + dt_lin(d) : c);
+                flags = root ? f_root : flags;
+                alpha = o.rgba ? o.pay >> 24 : alpha;
             });
             mine.cnt = cnt;
             mine.da  = (delta & 0xFFFFFFu) | alpha << 24;
@@ -306,33 +344,25 @@ namespace qb
         unsigned pc = kCPrev, pv = 0, n_ext = 0;
         {
             unsigned alpha = alpha_l, slot = slot_l;
-            dt_walk(words, byte0, my_entry, cend, [&](unsigned p, unsigned tag, unsigned pay) {
-                (void)p;
-                bool store = true;
-                if (tag == kOpRgb) {
-                    pc = kCConst, pv = (pay & 0xFFFFFFu) | alpha << 24, slot = slot_of(pv);  // speculated alpha, verified in W3
-                } else if (tag == kOpRgba) {
-                    pc = kCConst, pv = pay, alpha = pay >> 24, slot = slot_of(pay);
-                } else if ((tag >> 6) == 0) {
-                    const unsigned s = tag & 63u, c = myc[s];
-                    if (c == kCNone) {  // external read: what the table held in slot s when this lane began
-                        myc[s] = (unsigned char)(kCCached | s), myv[s * kDtRowV] = 0u;
-                        if (n_ext < (unsigned)kDtExt) sm.extc[n_ext * 32 + lane] = (unsigned char)s;
-                        ++n_ext;
-                        pc = s, pv = 0u;
-                    } else if (c & kCCached) {
-                        pc = s, pv = 0u;
-                    } else {
-                        pc = c, pv = myv[s * kDtRowV];
-                    }
-                    slot = s, store = false;  // storing the value it just read changes nothing
-                } else if ((tag >> 6) == 3) {
-                    store = false;  // OP_RUN: no table update (simple.cpp:156-163)
-                } else {
-                    const unsigned d = (tag >> 6) == 1 ? dt_diff_delta(tag) : dt_luma_delta(tag, pay);
-                    pv = add4(pv, d), slot = (slot + dt_lin(d)) & 63u;
+            dt_walk(words, byte0, mlo, mhi, [&](const DtOp& o) {
+                const unsigned d   = (o.tag >> 6) == 1 ? dt_diff_delta(o.tag) : dt_luma_delta(o.tag, o.pay);
+                const unsigned lit = o.rgba ? o.pay : (o.pay & 0xFFFFFFu) | alpha << 24;  // OP_RGB: speculated alpha, verified in W3
+                // OP_INDEX: what the column holds for the slot (an entry of this lane, a cached external read, or nothing yet)
+                const unsigned s  = o.tag & 63u;
+                const unsigned ic = myc[s], iv = myv[s * kDtRowV];
+                const bool     ext = o.index && ic == kCNone;  // external read: what the table held in slot s when this lane began
+                if (ext) {
+                    myc[s] = (unsigned char)(kCCached | s), myv[s * kDtRowV] = 0u;
+                    if (n_ext < (unsigned)kDtExt) sm.extc[n_ext * 32 + lane] = (unsigned char)s;
+                    ++n_ext;
                 }
-                if (store) myc[slot] = (unsigned char)pc, myv[slot * kDtRowV] = pv;
+                const bool own = o.index && ic < kCCached;  // stored by this lane before
+                const bool lit_op = o.rgb || o.rgba;
+                pc    = lit_op ? kCConst : (o.index ? (own ? ic : s) : pc);
+                pv    = lit_op ? lit : (o.index ? (own ? iv : 0u) : (o.delta ? add4(pv, d) : pv));
+                alpha = o.rgba ? o.pay >> 24 : alpha;
+                slot  = lit_op ? slot_of(lit) : (o.index ? s : (o.delta ? (slot + dt_lin(d)) & 63u : slot));
+                if (lit_op || o.delta) myc[slot] = (unsigned char)pc, myv[slot * kDtRowV] = pv;  // OP_INDEX / OP_RUN store nothing new
             });
         }
         if (n_ext > (unsigned)kDtExt) bad = true;
@@ -463,49 +493,72 @@ namespace qb
             unsigned prev = concrete(my_prev.code, my_prev.val), alpha = alpha_l, k_ext = 0;
             uint64_t pix = pix_base + pixoff;
             const unsigned tgt = D.target;
-            const bool     w32 = tgt == 4 && (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
-            dt_walk(words, byte0, my_entry, cend, [&](unsigned p, unsigned tag, unsigned pay) {
-                (void)p;
-                if (pix >= N) return;  // ops past the image are never executed by the reference
-                unsigned cur = prev, n = 1;
-                bool     store = true;
-                if (tag == kOpRgb) {  // simple.cpp:119-123: the alpha is inherited from the previous pixel
-                    cur = (pay & 0xFFFFFFu) | (prev & 0xFF000000u);
-                    if ((prev >> 24) != alpha) bad = true;
-                } else if (tag == kOpRgba) {
-                    cur = pay, alpha = pay >> 24;
-                } else if ((tag >> 6) == 0) {
-                    const unsigned s = tag & 63u;
-                    if (myc[s] == kCNone) {
-                        cur = k_ext < (unsigned)kDtExt ? concrete(sm.extc[k_ext * 32 + lane], sm.extv[k_ext * 32 + lane]) : 0u;
-                        ++k_ext;
-                        myc[s] = 0, myv[s * kDtRowV] = cur;
+            const bool     w32 = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+            // pixels leave in aligned groups of four (three or four 32-bit stores); q0..q2 hold the group under construction,
+            // `gstart` is the position in its group of the first pixel this lane owns
+            unsigned q0 = 0, q1 = 0, q2 = 0, gstart = (unsigned)pix & 3u;
+            auto store1 = [&](uint64_t i, unsigned v) {
+                if (tgt == 4 && w32) reinterpret_cast<unsigned*>(out)[i] = v;
+                else {
+                    uint8_t* d = out + i * tgt;
+                    d[0] = (uint8_t)v, d[1] = (uint8_t)(v >> 8), d[2] = (uint8_t)(v >> 16);
+                    if (tgt == 4) d[3] = (uint8_t)(v >> 24);
+                }
+            };
+            auto put = [&](unsigned cur) {
+                const unsigned ph = (unsigned)pix & 3u;
+                if (ph == 3u) {
+                    if (gstart == 0u && w32) {
+                        if (tgt == 4) {
+                            unsigned* d = reinterpret_cast<unsigned*>(out) + (pix - 3u);
+                            d[0] = q0, d[1] = q1, d[2] = q2, d[3] = cur;
+                        } else {
+                            unsigned* d = reinterpret_cast<unsigned*>(out + (pix - 3u) * 3u);
+                            d[0] = (q0 & 0xFFFFFFu) | q1 << 24;
+                            d[1] = ((q1 >> 8) & 0xFFFFu) | q2 << 16;
+                            d[2] = ((q2 >> 16) & 0xFFu) | cur << 8;
+                        }
                     } else {
-                        cur = myv[s * kDtRowV];
+                        for (unsigned j = gstart; j < 3u; ++j) store1(pix - 3u + j, j == 0 ? q0 : (j == 1 ? q1 : q2));
+                        store1(pix, cur);
                     }
-                    if (slot_of(cur) != s) bad = true;  // a never-stored (or mis-predicted) slot was read
-                    store = false;
-                } else if ((tag >> 6) == 3) {
-                    n = (tag & 63u) + 1u, store = false;
+                    gstart = 0u;
                 } else {
-                    cur = add4(prev, (tag >> 6) == 1 ? dt_diff_delta(tag) : dt_luma_delta(tag, pay));
+                    q0 = ph == 0u ? cur : q0, q1 = ph == 1u ? cur : q1, q2 = ph == 2u ? cur : q2;
                 }
-                if (store) {
-                    const unsigned s = slot_of(cur);
-                    myc[s] = 0, myv[s * kDtRowV] = cur;  // simple.cpp:169
+                ++pix;
+            };
+            dt_walk(words, byte0, mlo, mhi, [&](const DtOp& o) {
+                if (pix >= N) return;  // ops past the image are never executed by the reference
+                const unsigned d = (o.tag >> 6) == 1 ? dt_diff_delta(o.tag) : dt_luma_delta(o.tag, o.pay);
+                const unsigned s = o.tag & 63u;
+                const unsigned ic = myc[s], iv = myv[s * kDtRowV];
+                const bool     ext = o.index && ic == kCNone;
+                unsigned       xv = 0;
+                if (ext) {
+                    xv = k_ext < (unsigned)kDtExt ? concrete(sm.extc[k_ext * 32 + lane], sm.extv[k_ext * 32 + lane]) : 0u;
+                    ++k_ext;
+                    myc[s] = 0, myv[s * kDtRowV] = xv;
                 }
-                for (unsigned j = 0; j < n && pix < N; ++j, ++pix) {  // OP_RUN clamped to the image (simple.cpp:158)
-                    if (w32) reinterpret_cast<unsigned*>(out)[pix] = cur;
-                    else {
-                        uint8_t* d = out + pix * tgt;
-                        d[0] = (uint8_t)cur, d[1] = (uint8_t)(cur >> 8), d[2] = (uint8_t)(cur >> 16);
-                        if (tgt == 4) d[3] = (uint8_t)(cur >> 24);
-                    }
+                // simple.cpp:119-123: an OP_RGB inherits the alpha of the previous pixel
+                const unsigned cur = o.rgb ? (o.pay & 0xFFFFFFu) | (prev & 0xFF000000u)
+                                   : o.rgba ? o.pay
+                                   : o.index ? (ext ? xv : iv)
+                                   : o.delta ? add4(prev, d) : prev;
+                bad |= o.rgb && (prev >> 24) != alpha;     // the alpha W2 assumed for this literal
+                bad |= o.index && slot_of(cur) != s;       // a never-stored (or mis-predicted) slot was read
+                alpha = o.rgba ? o.pay >> 24 : alpha;
+                if (o.rgb || o.rgba || o.delta) {
+                    const unsigned ws = slot_of(cur);
+                    myc[ws] = 0, myv[ws * kDtRowV] = cur;  // simple.cpp:169
                 }
+                const unsigned n = o.run ? (o.tag & 63u) + 1u : 1u;
+                for (unsigned j = 0; j < n && pix < N; ++j) put(cur);  // OP_RUN clamped to the image (simple.cpp:158)
                 prev = cur;
             });
+            // pixels of an unfinished group
+            for (unsigned j = gstart; j < ((unsigned)pix & 3u); ++j) store1((pix & ~3ull) + j, j == 0 ? q0 : (j == 1 ? q1 : q2));
         }
-        QB_STAMP(desc, 71, 1, qb_t0);  // W3
         // the stream ended before the image (the reference decodes the zero padding on): general path
         if (t == ntiles - 1 && pix_base + n_pix < N) bad = true;
         if (t == ntiles - 1 && lane == 0) res->pixels = pix_base + n_pix < N ? pix_base + n_pix : N;

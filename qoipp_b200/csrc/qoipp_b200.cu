@@ -108,6 +108,7 @@ struct qoipp_b200_ctx {
     bool     attrs_set   = false;
     uint32_t ts_ticket = 0;  // encode_ts_kernel: current value of its ticket counter
     uint32_t dt_ticket = 0;  // decode_ts_kernel: likewise
+    bool     decode_ts = false;      // QOIPP_B200_DECODE_TS=1: thread-serial decode fast path (experimental, see decode_host.inl)
     bool     force_general = false;  // QOIPP_B200_GENERAL=1: always the general kernels (A/B measurements, tests)
     int      dec_coresident = 148;  // CTAs of decode_finish_kernel that fit on the device at once
 
@@ -305,6 +306,7 @@ extern "C"
         }
         c->sm_count = prop.multiProcessorCount;
         if (const char* g = std::getenv("QOIPP_B200_GENERAL")) c->force_general = g[0] == '1';
+        if (const char* g = std::getenv("QOIPP_B200_DECODE_TS")) c->decode_ts = g[0] == '1';
         *out        = c;
         return 0;
     }
