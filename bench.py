@@ -365,7 +365,7 @@ def main():
                          "decode_frac": round((alg / (dec_ms_max / args.steps * 1e-3) / 1e9) / peak, 5)},
             "e2e": {"value": round(e2e_gbps, 3), "unit": "GB/s", "h2d_bytes_per_step": (raw_one + e2e_enc) * e2e_imgs,
                     "d2h_bytes_per_step": (e2e_enc + raw_one) * e2e_imgs, "images_per_step": e2e_imgs},
-            "gpu_launches": 3 * args.steps, "clocks": clocks, "wall_s": round(t_wall, 3),
+            "gpu_launches": 4 * args.steps, "clocks": clocks, "wall_s": round(t_wall, 3),
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(args.workload, imgs, w, h, ch)
