@@ -83,6 +83,7 @@ namespace qb
 #define QB_DEC_SB 8
 #endif
     constexpr int kDecWarps = QB_DEC_WARPS, kDecThreads = kDecWarps * 32, kDecSB = QB_DEC_SB, kDecTB = kDecThreads * kDecSB;
+    constexpr int kDecMinCtas = kDecThreads * kDecSB >= 4096 ? 2 : 5;  // CTAs per SM the kernels are compiled for (shared memory bound)
     constexpr int kDecDescWords = 72;
     constexpr int kDwParse = 0, kDwPix = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
 
@@ -790,7 +791,7 @@ namespace qb
     }
 
     // round 0: one tile per CTA
-    __global__ void __launch_bounds__(kDecThreads, 5) decode_kernel(const DecParams P)
+    __global__ void __launch_bounds__(kDecThreads, kDecMinCtas) decode_kernel(const DecParams P)
     {
         DecSmem& sm = *reinterpret_cast<DecSmem*>(QB_DYN_SMEM);
         if (threadIdx.x == 0) sm.ticket = atomicInc(P.ticket, P.n_tiles - 1u);
@@ -948,7 +949,7 @@ namespace qb
     // verified costs a single empty launch): rounds 1..kDecRounds re-decode, per image, the tiles from the first refuted
     // one on with the alphas learned by the round before (grid-wide barrier between rounds); what still fails after the
     // last round is decoded by the sequential loop, one warp per image, resuming behind the last verified tile.
-    __global__ void __launch_bounds__(kDecThreads, 5) decode_finish_kernel(const DecParams P)
+    __global__ void __launch_bounds__(kDecThreads, kDecMinCtas) decode_finish_kernel(const DecParams P)
     {
         DecSmem& sm = *reinterpret_cast<DecSmem*>(QB_DYN_SMEM);
         if (P.fast_used && P.control->fast_any_bad) {  // same value in every CTA: final when this kernel starts

@@ -78,6 +78,48 @@ namespace qb
         len   = alpha_ne ? 5u : (diff_ok ? 1u : (luma_ok ? 2u : 4u));
     }
 
+    // G consecutive pixels of a lane's chunk (group g) from global memory.  Complete chunks use 16-byte loads; in the image's
+    // last tile pixels past the end repeat the last valid one (`lastv`), so they never differ and `vmask` drops them.
+    template <int CH, int G>
+    __device__ __forceinline__ void ts_load_group(const uint8_t* in_img, uint64_t g0, unsigned g, unsigned nvalid, unsigned& lastv,
+                                                  unsigned (&px)[G])
+    {
+        if (nvalid == (unsigned)kTsK) {
+            if (CH == 4) {
+                const uint4* src = reinterpret_cast<const uint4*>(in_img + g0 * 4) + g * (G / 4);
+#pragma unroll
+                for (int j = 0; j < G / 4; ++j) {
+                    const uint4 v = __ldg(src + j);
+                    px[4 * j] = v.x, px[4 * j + 1] = v.y, px[4 * j + 2] = v.z, px[4 * j + 3] = v.w;
+                }
+            } else {
+                const uint2* src = reinterpret_cast<const uint2*>(in_img + g0 * 3) + g * (3 * G / 8);  // 3 G bytes, 8-byte aligned
+                unsigned     wd[3 * G / 4];
+#pragma unroll
+                for (int j = 0; j < 3 * G / 8; ++j) {
+                    const uint2 v = __ldg(src + j);
+                    wd[2 * j] = v.x, wd[2 * j + 1] = v.y;
+                }
+#pragma unroll
+                for (int j = 0; j < G / 4; ++j) {  // four pixels from three words; util.hpp:325: alpha forced to 255
+                    const unsigned a = wd[3 * j], b = wd[3 * j + 1], c = wd[3 * j + 2];
+                    px[4 * j]     = a | 0xFF000000u;
+                    px[4 * j + 1] = __funnelshift_r(a, b, 24) | 0xFF000000u;
+                    px[4 * j + 2] = __funnelshift_r(b, c, 16) | 0xFF000000u;
+                    px[4 * j + 3] = (c >> 8) | 0xFF000000u;
+                }
+            }
+            lastv = px[G - 1];
+        } else {
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const unsigned k = g * G + i;
+                if (k < nvalid) lastv = load_pixel<CH>(in_img, g0 + k, true);
+                px[i] = lastv;
+            }
+        }
+    }
+
     // ---- encode role: tile `gt` (global tile index) -> scratch record + carry words.  One warp.
     template <int CH>
     __device__ __forceinline__ void ts_encode_tile(const EncParams& P, TsWarpSmem& sm, unsigned gt)
@@ -99,71 +141,48 @@ namespace qb
         const unsigned  nvalid     = first >= n_here ? 0u : min((unsigned)K, n_here - first);
         const uint64_t  g0         = tile_start + first;
 
-        // ---- this lane's 32 pixels
-        unsigned px[K];
-        if (nvalid == (unsigned)K) {
-            if (CH == 4) {
-                const uint4* src = reinterpret_cast<const uint4*>(in_img + g0 * 4);
-#pragma unroll
-                for (int j = 0; j < K / 4; ++j) {
-                    const uint4 v = __ldg(src + j);
-                    px[4 * j] = v.x, px[4 * j + 1] = v.y, px[4 * j + 2] = v.z, px[4 * j + 3] = v.w;
-                }
-            } else {
-                const uint4* src = reinterpret_cast<const uint4*>(in_img + g0 * 3);
-                unsigned     wd[3 * K / 4];
-#pragma unroll
-                for (int j = 0; j < 3 * K / 16; ++j) {
-                    const uint4 v = __ldg(src + j);
-                    wd[4 * j] = v.x, wd[4 * j + 1] = v.y, wd[4 * j + 2] = v.z, wd[4 * j + 3] = v.w;
-                }
-#pragma unroll
-                for (int j = 0; j < K / 4; ++j) {  // four pixels from three words; util.hpp:325: alpha forced to 255
-                    const unsigned a = wd[3 * j], b = wd[3 * j + 1], c = wd[3 * j + 2];
-                    px[4 * j]     = a | 0xFF000000u;
-                    px[4 * j + 1] = __funnelshift_r(a, b, 24) | 0xFF000000u;
-                    px[4 * j + 2] = __funnelshift_r(b, c, 16) | 0xFF000000u;
-                    px[4 * j + 3] = (c >> 8) | 0xFF000000u;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k) px[k] = (unsigned)k < nvalid ? load_pixel<CH>(in_img, g0 + k, true) : 0u;
-        }
-        // own table column: nothing stored yet (sentinel(s)); issued behind the pixel loads so that it overlaps their latency
+        // The chunk is walked in groups of G pixels (loops, not 32 unrolled copies: unrolled, the kernel was 80 KB of code and
+        // instruction fetch was its largest stall, ncu no_instruction 2.7 per issued instruction); W1 and W3 each read the
+        // pixels once, the second time from L2.
+        constexpr int G = 8, NG = K / G;
+        // neighbours across the chunk boundary and the first group; the loads are in flight while the column is initialised
+        const unsigned prev0 = g0 == 0 ? kStartPixel : (g0 <= N ? load_pixel<CH>(in_img, g0 - 1, true) : 0u);
+        const unsigned nxt   = g0 + K < N ? load_pixel<CH>(in_img, g0 + K, true) : 0u;
+        unsigned       px[G], nx[G];
+        unsigned       lastv = prev0;
+        ts_load_group<CH, G>(in_img, g0, 0u, nvalid, lastv, px);
+        // own table column: nothing stored yet (sentinel(s))
 #pragma unroll
         for (int s = 0; s < 64; ++s) sm.tab[s * R + lane] = s == 0 ? 1u : 0u;
-        // neighbours across the chunk boundary
-        const unsigned up = __shfl_up_sync(kFull, px[K - 1], 1);
-        const unsigned dn = __shfl_down_sync(kFull, px[0], 1);
-        unsigned       prev0 = up, nxt = dn;
-        if (lane == 0) prev0 = g0 == 0 ? kStartPixel : (g0 <= N ? load_pixel<CH>(in_img, g0 - 1, true) : 0u);
-        if (lane == 31) nxt = g0 + K < N ? load_pixel<CH>(in_img, g0 + K, true) : 0u;
-        if (nvalid != (unsigned)K) {  // pixels past the image repeat the last one: they never differ, `vmask` drops them
-            unsigned lastv = prev0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if ((unsigned)k < nvalid) lastv = px[k];
-                else px[k] = lastv;
-            }
-        }
-        const bool nexteq_last = g0 + K < N && nxt == px[K - 1];  // does a run continue into the next lane's chunk?
-        QB_STAMP(desc, 66, 0, qb_t0);  // pixels loaded
+        QB_STAMP(desc, 66, 0, qb_t0);  // setup
 
         // ================= W1: per-slot last store of this chunk, mask of differing pixels =================
-        unsigned neMask = 0;
+        unsigned neMask = 0, last_px;
         {
             unsigned p = prev0;
+#pragma unroll 1
+            for (int g = 0; g < NG; ++g) {
+                if (g + 1 < NG) ts_load_group<CH, G>(in_img, g0, (unsigned)g + 1u, nvalid, lastv, nx);  // in flight during this group
+                unsigned bits = 0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const unsigned cur = px[k];
-                if (cur != p) {
-                    neMask |= 1u << k;
-                    sm.tab[slot_of(cur) * R + lane] = cur;  // simple.cpp:54-57: every differing pixel ends up in its slot
+                for (int i = 0; i < G; ++i) {
+                    const unsigned cur = px[i];
+                    if (cur != p) {
+                        bits |= 1u << i;
+                        sm.tab[slot_of(cur) * R + lane] = cur;  // simple.cpp:54-57: every differing pixel ends up in its slot
+                    }
+                    p = cur;
                 }
-                p = cur;
+                neMask |= bits << (g * G);
+#pragma unroll
+                for (int i = 0; i < G; ++i) px[i] = nx[i];
             }
+            last_px = p;
         }
+        const bool nexteq_last = g0 + K < N && nxt == last_px;  // does a run continue into the next lane's chunk?
+        // the first group of the second pass is fetched (from L2 now) before the merge and the look-backs, not after them
+        lastv = prev0;
+        ts_load_group<CH, G>(in_img, g0, 0u, nvalid, lastv, px);
         const unsigned vmask  = nvalid == (unsigned)K ? 0xFFFFFFFFu : (1u << nvalid) - 1u;
         const unsigned eqMask = ~neMask & vmask;
         // last differing pixel before this lane's chunk (tile-local index + 1, 0 = none): exclusive max-scan
@@ -262,41 +281,49 @@ namespace qb
         unsigned        nw = 0, fill = 0, alo = 0, ahi = 0;  // whole words stored, bytes pending in alo (ahi: overflow of one append)
         {
             unsigned p = prev0;
+#pragma unroll 1
+            for (int g = 0; g < NG; ++g) {
+                if (g + 1 < NG) ts_load_group<CH, G>(in_img, g0, (unsigned)g + 1u, nvalid, lastv, nx);
+                const unsigned nm = neMask >> (g * G), em = eqMask >> (g * G);
+                const bool     nexteq_g = g + 1 < NG ? ((em >> G) & 1u) != 0 : nexteq_last;  // for the group's last pixel
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const unsigned cur = px[k];
-                const bool     ne  = (neMask >> k) & 1u, eq = (eqMask >> k) & 1u;
-                const bool     nexteq = k < K - 1 ? ((eqMask >> (k < K - 1 ? k + 1 : k)) & 1u) != 0 : nexteq_last;
-                // run pixel: one byte when the counter reaches 62 or the run ends here (simple.cpp:39-49, 91-94)
-                const unsigned r1   = r + 1u;
-                const bool     full = r1 == kRunLimit;
-                const bool     emit = eq && (full || !nexteq);
-                r                   = (eq && !full) ? r1 : 0u;
-                unsigned chunk, len;
-                ts_colour_chunk<CH>(cur, p, chunk, len);
-                // table probe and store (simple.cpp:51-57); an entry this tile has not stored yet holds the sentinel
-                const unsigned slot = slot_of(cur);
-                unsigned*      te   = sm.tab + slot * R + lane;
-                unsigned       tv   = *te;
-                if (tv == (slot == 0 ? 1u : 0u)) tv = sm.gin[slot];
-                if (ne) *te = cur;
-                const bool hit = tv == cur;
-                chunk = ne ? (hit ? (kOpIndex | slot) : chunk) : (emit ? (kOpRun - 1u) + r1 : 0u);  // util.hpp:190-235
-                len   = ne ? (hit ? 1u : len) : (emit ? 1u : 0u);
-                // append
-                const unsigned sh = fill * 8u;
-                alo |= chunk << sh;
-                ahi = __funnelshift_l(chunk, (CH == 4 && len == 5u) ? cur >> 24 : 0u, sh);
-                fill += len;
-                if (fill >= 4u) {
-                    priv[nw * 32] = alo;
-                    ++nw, alo = ahi, fill -= 4u;
-                    if (CH == 4 && fill >= 4u) {  // a five-byte chunk behind three pending bytes fills two words
+                for (int i = 0; i < G; ++i) {
+                    const unsigned cur = px[i];
+                    const bool     ne  = (nm >> i) & 1u, eq = (em >> i) & 1u;
+                    const bool     nexteq = i < G - 1 ? ((em >> (i < G - 1 ? i + 1 : i)) & 1u) != 0 : nexteq_g;
+                    // run pixel: one byte when the counter reaches 62 or the run ends here (simple.cpp:39-49, 91-94)
+                    const unsigned r1   = r + 1u;
+                    const bool     full = r1 == kRunLimit;
+                    const bool     emit = eq && (full || !nexteq);
+                    r                   = (eq && !full) ? r1 : 0u;
+                    unsigned chunk, len;
+                    ts_colour_chunk<CH>(cur, p, chunk, len);
+                    // table probe and store (simple.cpp:51-57); an entry this tile has not stored yet holds the sentinel
+                    const unsigned slot = slot_of(cur);
+                    unsigned*      te   = sm.tab + slot * R + lane;
+                    unsigned       tv   = *te;
+                    if (tv == (slot == 0 ? 1u : 0u)) tv = sm.gin[slot];
+                    if (ne) *te = cur;
+                    const bool hit = tv == cur;
+                    chunk = ne ? (hit ? (kOpIndex | slot) : chunk) : (emit ? (kOpRun - 1u) + r1 : 0u);  // util.hpp:190-235
+                    len   = ne ? (hit ? 1u : len) : (emit ? 1u : 0u);
+                    // append
+                    const unsigned sh = fill * 8u;
+                    alo |= chunk << sh;
+                    ahi = __funnelshift_l(chunk, (CH == 4 && len == 5u) ? cur >> 24 : 0u, sh);
+                    fill += len;
+                    if (fill >= 4u) {
                         priv[nw * 32] = alo;
-                        ++nw, alo = 0u, fill -= 4u;
+                        ++nw, alo = ahi, fill -= 4u;
+                        if (CH == 4 && fill >= 4u) {  // a five-byte chunk behind three pending bytes fills two words
+                            priv[nw * 32] = alo;
+                            ++nw, alo = 0u, fill -= 4u;
+                        }
                     }
+                    p = cur;
                 }
-                p = cur;
+#pragma unroll
+                for (int i = 0; i < G; ++i) px[i] = nx[i];
             }
             priv[nw * 32] = alo;  // the partial last word (its upper bytes are zero)
         }
@@ -436,6 +463,8 @@ namespace qb
         const unsigned lane    = threadIdx.x & 31u;
         const unsigned n_tiles = P.tiles_per_image * P.n_images;
         for (;;) {
+            // the ticket is drawn when the tile starts, never earlier: a claimed tile that is not running yet would stall
+            // the look-backs of all its successors (measured: drawing one tile ahead to prefetch its pixels cost 20 %)
             unsigned x = 0;
             if (lane == 0) x = atomicAdd(P.ticket, 1u) - P.ticket_base[0];
             x = __shfl_sync(kFull, x, 0);
