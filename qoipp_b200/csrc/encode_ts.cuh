@@ -387,25 +387,33 @@ namespace qb
         {
             // destination word m (from the word holding my first byte) = my bytes 4m - a .. 4m - a + 3: slice words m - 1 and m
             // funnel-shifted; only the first and the last destination word can be shared with a neighbour (byte stores).
-            // All slice words are loaded up front (one round trip), the rest runs out of registers.
-            constexpr int  PW = C::kPrivWords;
             const unsigned a = off & 3u, rs = 32u - a * 8u;
             unsigned*      d32 = reinterpret_cast<unsigned*>(stage) + (off >> 2);
-            const unsigned nwp = (total + 3u) >> 2;      // slice words holding bytes
-            const unsigned nd  = (total + a + 3u) >> 2;  // destination words touched (<= PW)
-            unsigned       hw[PW];
+            const unsigned nwp = (total + 3u) >> 2;                       // slice words holding bytes
+            const unsigned nd  = total ? (total + a + 3u) >> 2 : 0u;      // destination words touched
+            const unsigned maxnd = __reduce_max_sync(kFull, nd);          // the warp walks the longest slice, eight words a round
+            unsigned       cw[8], nx[8], lo = 0, v_first = 0, v_last = 0;
 #pragma unroll
-            for (int i = 0; i < PW; ++i) hw[i] = (unsigned)i < nwp ? priv[i * 32] : 0u;
-            unsigned v_first = 0, v_last = 0;
+            for (int i = 0; i < 8; ++i) cw[i] = (unsigned)i < nwp ? priv[i * 32] : 0u;
+            for (unsigned m0 = 0; m0 < maxnd; m0 += 8u) {
+                if (m0 + 8u < maxnd) {  // the next round's words are in flight during this one
 #pragma unroll
-            for (int m = 0; m < PW; ++m) {
-                const unsigned v = __funnelshift_rc(m ? hw[m ? m - 1 : 0] : 0u, hw[m], rs);
-                if ((unsigned)m < nd) {
-                    const bool whole = (m > 0 || a == 0) && 4u * m + 4u <= total + a;
-                    if (whole) d32[m] = v;
-                    else if (m == 0) v_first = v;
-                    else v_last = v;
+                    for (int i = 0; i < 8; ++i) nx[i] = m0 + 8u + i < nwp ? priv[(m0 + 8u + i) * 32] : 0u;
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned m = m0 + i;
+                    const unsigned v = __funnelshift_rc(lo, cw[i], rs);
+                    lo               = cw[i];
+                    if (m < nd) {
+                        const bool whole = (m > 0 || a == 0) && 4u * m + 4u <= total + a;
+                        if (whole) d32[m] = v;
+                        else if (m == 0) v_first = v;
+                        else v_last = v;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cw[i] = nx[i];
             }
             auto partial = [&](unsigned m, unsigned v) {
                 const unsigned b0 = m == 0 ? a : 0u, b1 = min(4u, total + a - 4u * m);
@@ -476,7 +484,7 @@ namespace qb
 
     // Copy kernel: one warp per tile, launched behind the encode kernel on the same stream.
     template <int CH>
-    __global__ void __launch_bounds__(kTsCopyWarps * 32) encode_ts_copy_kernel(const EncParams P)
+    __global__ void __launch_bounds__(kTsCopyWarps * 32, 5) encode_ts_copy_kernel(const EncParams P)
     {
         TsCopySmem&    sm = reinterpret_cast<TsCopySmem*>(QB_DYN_SMEM)[threadIdx.x >> 5];
         const unsigned gt = blockIdx.x * kTsCopyWarps + (threadIdx.x >> 5);
