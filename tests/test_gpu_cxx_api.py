@@ -21,3 +21,27 @@ def test_cxx_api_replays_reference_tests(tmp_path):
     print(r.stdout[-2000:], r.stderr[-4000:])
     assert r.returncode == 0, r.stderr[-4000:]
     assert " 0 failed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_qoiconv_round_trip_on_disk(tmp_path):
+    """examples/qoiconv (02_conv.cpp analogue): raw -> .qoi -> raw through the file overloads of the C++ API."""
+    from oracle.pyoracle import Oracle
+    from qoipp_b200 import synth
+
+    subprocess.run(["make", "-C", os.path.join(ROOT, "qoipp_b200", "csrc", "cxx")], check=True, stdout=subprocess.DEVNULL)
+    tool = os.path.join(ROOT, "examples", "qoiconv")
+    for ch in (3, 4):
+        w, h = 300, 217
+        raw = synth.generate("photo", w, h, ch)
+        raw.tofile(tmp_path / "in.raw")
+        r = subprocess.run([tool, "encode", str(tmp_path / "in.raw"), str(w), str(h), str(ch), str(tmp_path / "a.qoi")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert np.array_equal(np.fromfile(tmp_path / "a.qoi", dtype=np.uint8), Oracle.encode(raw, w, h, ch))
+        r = subprocess.run([tool, "info", str(tmp_path / "a.qoi")], capture_output=True, text=True)
+        assert r.returncode == 0 and f"{w} x {h}, {ch} channels" in r.stdout, r.stdout + r.stderr
+        r = subprocess.run([tool, "decode", str(tmp_path / "a.qoi"), str(tmp_path / "out.raw")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert np.array_equal(np.fromfile(tmp_path / "out.raw", dtype=np.uint8), raw)
+    r = subprocess.run([tool, "info", str(tmp_path / "in.raw")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Not a QOI file" in r.stderr
