@@ -117,7 +117,7 @@ extern "C"
         uint8_t*       d_out = mapped_host(h_out);
         if (!d_in) {
             QB_CUDA(c->stage_in.reserve(qoi_size + 64));
-            QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_qoi, qoi_size, cudaMemcpyDefault, s));
+            QB_CUDA(pageable_to_device(c, c->stage_in.p, h_qoi, qoi_size, s));
             d_in = static_cast<uint8_t*>(c->stage_in.p);
         }
         const bool staged_out = d_out == nullptr;
@@ -126,8 +126,8 @@ extern "C"
             d_out = static_cast<uint8_t*>(c->stage_out.p);
         }
         if (int32_t e = qoipp_b200_decode_dev(c, d_in, qoi_size, desc, (uint8_t)tgt, flip, d_out, need, s)) return e;
-        if (staged_out) QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, need, cudaMemcpyDefault, s));
-        QB_CUDA(cudaStreamSynchronize(s));
+        if (staged_out) QB_CUDA(device_to_pageable(c, h_out, c->stage_out.p, need, s));
+        else QB_CUDA(cudaStreamSynchronize(s));
         desc->channels = (uint8_t)tgt;  // :476 the returned Desc carries the target
         return 0;
     }
