@@ -709,29 +709,33 @@ namespace qb
                 const unsigned cn   = min(pch, total - c0);
                 uint8_t*       gdst = out + (pix_base + c0) * tgt;
                 const unsigned sh   = (unsigned)(reinterpret_cast<uintptr_t>(gdst) & 15u);
-                if (total <= pch && tgt == 4 && (sh & 3u) == 0) {
-                    // common case: the whole tile fits one staging round and pixels are word aligned
+                if (total <= pch && (tgt == 3 || (sh & 3u) == 0)) {
+                    // common case: the whole tile fits one staging round (and four-byte pixels are word aligned).  Every op
+                    // stores its own pixel; the pixels of an OP_RUN (clamped to the image, simple.cpp:158) are written by the
+                    // whole warp, 32 at a time -- one lane looping over its run kept the other 31 waiting (measured: 7 % of
+                    // the kernel's instructions at a fifth of the lanes).
                     unsigned* s32 = reinterpret_cast<unsigned*>(stg + sh);
-                    for (unsigned k = tid; k < n_ops; k += kDecThreads) {
-                        const unsigned meta = sm.op_meta[k], val = sm.op_val[k];
-                        const unsigned p0 = meta & 0x1FFFFu, np1 = (meta >> 17) & 63u;
-                        if (p0 < total) s32[p0] = val;
-                        if (np1)  // OP_RUN, clamped to the image (simple.cpp:158)
-                            for (unsigned j = 1; j <= np1 && p0 + j < total; ++j) s32[p0 + j] = val;
-                    }
-                } else if (total <= pch && tgt == 3) {
-                    for (unsigned k = tid; k < n_ops; k += kDecThreads) {
-                        const unsigned meta = sm.op_meta[k], val = sm.op_val[k];
-                        const unsigned p0 = meta & 0x1FFFFu, np1 = (meta >> 17) & 63u;
-                        if (p0 < total) {  // the op's own pixel: straight-line for every lane (measured: the shared loop ran at 20 % lane use)
-                            unsigned char* d = stg + sh + p0 * 3u;
+                    auto put = [&](unsigned p, unsigned val) {
+                        if (tgt == 4) s32[p] = val;
+                        else {
+                            unsigned char* d = stg + sh + p * 3u;
                             d[0] = (unsigned char)val, d[1] = (unsigned char)(val >> 8), d[2] = (unsigned char)(val >> 16);
                         }
-                        if (np1)  // OP_RUN, clamped to the image (simple.cpp:158)
-                            for (unsigned j = 1; j <= np1 && p0 + j < total; ++j) {
-                                unsigned char* d = stg + sh + (p0 + j) * 3u;
-                                d[0] = (unsigned char)val, d[1] = (unsigned char)(val >> 8), d[2] = (unsigned char)(val >> 16);
-                            }
+                    };
+                    const unsigned lane_ = tid & 31u;
+                    for (unsigned kb = tid - lane_; kb < n_ops; kb += kDecThreads) {  // uniform per warp
+                        const unsigned k     = kb + lane_;
+                        const bool     valid = k < n_ops;
+                        const unsigned meta = valid ? sm.op_meta[k] : 0u, val = valid ? sm.op_val[k] : 0u;
+                        const unsigned p0 = meta & 0x1FFFFu, np1 = (meta >> 17) & 63u;
+                        if (valid && p0 < total) put(p0, val);
+                        unsigned runs = __ballot_sync(kFull, valid && np1 != 0);
+                        while (runs) {
+                            const int src = __ffs((int)runs) - 1;
+                            runs &= runs - 1u;
+                            const unsigned rp = __shfl_sync(kFull, p0, src), rn = __shfl_sync(kFull, np1, src), rv = __shfl_sync(kFull, val, src);
+                            for (unsigned j = 1u + lane_; j <= rn && rp + j < total; j += 32u) put(rp + j, rv);
+                        }
                     }
                 } else
                 for (unsigned k = tid; k < n_ops; k += kDecThreads) {
