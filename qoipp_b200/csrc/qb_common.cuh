@@ -188,9 +188,10 @@ namespace qb
                 if (pending == 0) break;
                 QB_SPIN_YIELD();
             }
+            if (first == 0u) return comb(shfl_T(v, 0), acc);  // the direct predecessor is inclusive already: no fold
             if (st == ST_AGG_EMPTY || st == ST_NONE || lane > first) v = empty;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
+            // ordered fold over lanes 0 .. first (lane 0 is the latest tile): only as many steps as that span needs
+            for (unsigned d = 1; d <= min(first, 31u); d <<= 1) {
                 const T o = shfl_down_T(v, d);
                 if (lane + d < 32u) v = comb(o, v);
             }
