@@ -150,7 +150,7 @@ namespace qb
     }
     __device__ __forceinline__ unsigned dt_lin(unsigned d) { return __dp4a(d, 0x00070503u, 0u) & 63u; }
 
-    // one tile, one warp.  Returns false when the image has to take the general path.
+    // one tile, one warp; flags the image (DecResult::pad[0]) when it has to take the general path
     __device__ __forceinline__ void dt_decode_tile(const DtParams& P, DtWarpSmem& sm, unsigned gt)
     {
         const DecParams& D    = P.d;
