@@ -5,59 +5,33 @@ namespace
     constexpr size_t kCtrlBytes = 64;  // DecControl lives in front of the DecResult array
     static_assert(sizeof(DecControl) <= kCtrlBytes, "control block");
 
-    // fast_tiles: tiles of decode_ts_kernel (0 = general kernel only); d_fast_first: per-image first fast tile (batch)
-    int32_t launch_decode(qoipp_b200_ctx* c, DecParams& P, cudaStream_t s, uint64_t fast_tiles = 0, const uint32_t* d_fast_first = nullptr)
+    int32_t launch_decode(qoipp_b200_ctx* c, DecParams& P, cudaStream_t s)
     {
         QB_CUDA(set_attrs(c));
-        QB_CUDA(c->tickets.reserve(64, true));
+        if (P.n_pixels >= kPixSat) return H::TooBig;  // the pixel carry word holds 33 bits
         const size_t res_bytes = kCtrlBytes + sizeof(DecResult) * P.n_images;
-        QB_CUDA(c->results.reserve(res_bytes));
+        QB_CUDA(c->results.reserve(res_bytes, s));
         QB_CUDA(cudaMemsetAsync(c->results.p, 0, res_bytes, s));
-        QB_CUDA(c->fix.reserve((size_t)P.n_tiles * kFixWords * sizeof(uint32_t)));
+        QB_CUDA(c->fix.reserve((size_t)P.n_tiles * kFixWords * sizeof(uint32_t), s, true));
         // one epoch per possible round; the learned-alpha lists are tagged with the first one
-        const uint64_t gen_bytes = (uint64_t)P.n_tiles * kDecDescWords * sizeof(uint64_t);
-        QB_CUDA(c->next_epoch(gen_bytes + fast_tiles * kDecDescWords * sizeof(uint64_t), s, kDecRounds + 1));
-        P.epoch     = c->epoch;
-        P.round     = 0;
-        P.control   = static_cast<DecControl*>(c->results.p);
-        P.results   = reinterpret_cast<DecResult*>(static_cast<uint8_t*>(c->results.p) + kCtrlBytes);
-        P.desc      = static_cast<uint64_t*>(c->carry.p);
-        P.fix       = static_cast<uint32_t*>(c->fix.p);
-        P.ticket    = static_cast<uint32_t*>(c->tickets.p) + 1;
-        P.fast_used = fast_tiles != 0;
-        if (fast_tiles) {
-            // thread-serial fast path (decode_ts.cuh): persistent warps; images it cannot verify are flagged and decoded by
-            // the general machinery inside decode_finish_kernel
-            DtParams F{};
-            F.d = P, F.tile_first = d_fast_first;
-            F.desc        = P.desc + (uint64_t)P.n_tiles * kDecDescWords;
-            F.n_tiles     = (uint32_t)fast_tiles;
-            F.ticket      = static_cast<uint32_t*>(c->tickets.p) + 10;
-            F.ticket_base = c->dt_ticket;
-            const unsigned n_ctas = (unsigned)std::min<uint64_t>((fast_tiles + kDtWarps - 1) / kDtWarps, (uint64_t)c->sm_count * QB_DT_CTAS);
-            c->dt_ticket += (uint32_t)fast_tiles + n_ctas * kDtWarps;
-            decode_ts_kernel<<<n_ctas, kDtThreads, kDtWarps * sizeof(DtWarpSmem), s>>>(F);
-        } else {
-            decode_kernel<<<P.n_tiles, kDecThreads, sizeof(DecSmem), s>>>(P);
-        }
+        QB_CUDA(c->next_epoch((uint64_t)P.n_tiles * kDecDescWords * sizeof(uint64_t), s, kDecRounds + 1));
+        P.epoch   = c->epoch;
+        P.round   = 0;
+        P.control = static_cast<DecControl*>(c->results.p);
+        P.results = reinterpret_cast<DecResult*>(static_cast<uint8_t*>(c->results.p) + kCtrlBytes);
+        P.desc    = static_cast<uint64_t*>(c->carry.p);
+        P.fix     = static_cast<uint32_t*>(c->fix.p);
+        // persistent warps: one CTA per resident slot
+        const unsigned want   = (P.n_tiles + kWtWarps - 1) / kWtWarps;
+        const unsigned n_ctas = std::max(1u, std::min<unsigned>(want, (unsigned)c->dec_coresident));
+        decode_wt_kernel<<<n_ctas, kWtThreads, kWtSmemBytes, s>>>(P);
         QB_CUDA(cudaGetLastError());
         // Retry rounds and the sequential part are ONE cooperative launch enqueued unconditionally: it returns at once when
         // round 0 verified every tile -- no host round trip, a few microseconds when nothing is to be done.
-        const unsigned grid = std::min<unsigned>(P.n_tiles, (unsigned)c->dec_coresident);
-        void*          args[] = { &P };
-        QB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_finish_kernel), dim3(grid), dim3(kDecThreads), args,
-                                            sizeof(DecSmem), s));
+        void* args[] = { &P };
+        QB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_finish_kernel), dim3(n_ctas), dim3(kWtThreads), args,
+                                            kWtSmemBytes, s));
         return 0;
-    }
-
-    // decode_ts_kernel (decode_ts.cuh) is opt-in (QOIPP_B200_DECODE_TS=1): exact and verified, but measured SLOWER than the
-    // general kernel in round 1 (4K RGB photo 321-407 us against 278 us: 18.6 KB of shared memory per warp leave 12 warps per
-    // SM, and three serial op walks cost as many instructions as the general kernel's phases; profiles/r01_experiments.md).
-    // It walks every lane's 68 stream bytes serially, long runs included, so streams that are mostly OP_RUN (less than a
-    // quarter byte per pixel) stay on the general kernel in any case.
-    bool use_fast_decode(const qoipp_b200_ctx* c, uint64_t stream_bytes, uint64_t pixels, bool flip)
-    {
-        return c->decode_ts && !c->force_general && !flip && stream_bytes * 4 >= pixels;
     }
 }
 
@@ -83,8 +57,7 @@ extern "C"
         P.out = d_out, P.out_stride = 0, P.n_pixels = n;
         P.width = desc->width, P.height = desc->height, P.target = tgt, P.flip = flip != 0;
         P.n_images = 1, P.n_tiles = (uint32_t)tiles;
-        const uint64_t fast = use_fast_decode(c, qoi_size, n, flip != 0) ? (qoi_size - H::kHeaderSize + kDtTB - 1) / kDtTB : 0;
-        return launch_decode(c, P, static_cast<cudaStream_t>(stream), fast);
+        return launch_decode(c, P, static_cast<cudaStream_t>(stream));
     }
 
     int32_t qoipp_b200_decode_status(qoipp_b200_ctx* c, void* stream, int32_t* path)
@@ -94,7 +67,7 @@ extern "C"
         auto* h = static_cast<DecResult*>(c->h_result.p);
         QB_CUDA(cudaMemcpyAsync(h, static_cast<uint8_t*>(c->results.p) + kCtrlBytes, 64, cudaMemcpyDeviceToHost, s));
         QB_CUDA(cudaStreamSynchronize(s));
-        if (path) *path = (int32_t)h->path + (h->pad[0] ? 1000 : 0);
+        if (path) *path = (int32_t)h->path;
         return 0;
     }
 
@@ -116,13 +89,13 @@ extern "C"
         const uint8_t* d_in  = mapped_host(h_qoi);  // page-locked buffers are used in place (zero-copy over PCIe)
         uint8_t*       d_out = mapped_host(h_out);
         if (!d_in) {
-            QB_CUDA(c->stage_in.reserve(qoi_size + 64));
+            QB_CUDA(c->stage_in.reserve(qoi_size + 64, s));
             QB_CUDA(pageable_to_device(c, c->stage_in.p, h_qoi, qoi_size, s));
             d_in = static_cast<uint8_t*>(c->stage_in.p);
         }
         const bool staged_out = d_out == nullptr;
         if (staged_out) {
-            QB_CUDA(c->stage_out.reserve(need + 64));
+            QB_CUDA(c->stage_out.reserve(need + 64, s));
             d_out = static_cast<uint8_t*>(c->stage_out.p);
         }
         if (int32_t e = qoipp_b200_decode_dev(c, d_in, qoi_size, desc, (uint8_t)tgt, flip, d_out, need, s)) return e;
@@ -146,23 +119,21 @@ extern "C"
         Guard g(c->device);
         auto  s = static_cast<cudaStream_t>(stream);
         // per-image tile ranges: offsets (u64) then first-tile ids (u32), staged through pinned memory
-        const size_t off_bytes = sizeof(uint64_t) * (n_images + 1), tf_bytes = 2 * sizeof(uint32_t) * (n_images + 1);
+        const size_t off_bytes = sizeof(uint64_t) * (n_images + 1), tf_bytes = sizeof(uint32_t) * (n_images + 2);
         QB_CUDA(c->h_pin_in.reserve(off_bytes + tf_bytes));
-        QB_CUDA(c->aux.reserve(off_bytes + tf_bytes));
+        QB_CUDA(c->aux.reserve(off_bytes + tf_bytes, s));
         QB_CUDA(cudaStreamSynchronize(s));  // the pinned table of an earlier call may still be in flight
         auto*    ho = static_cast<uint64_t*>(c->h_pin_in.p);
         auto*    ht = reinterpret_cast<uint32_t*>(ho + n_images + 1);
-        auto*    hf = ht + n_images + 1;  // first tile of every image for decode_ts_kernel
-        uint64_t tiles = 0, ftiles = 0;
+        uint64_t tiles = 0;
         for (uint32_t k = 0; k < n_images; ++k) {
             const uint64_t sz = h_offsets[k + 1] - h_offsets[k];
             if (sz <= H::kHeaderSize + H::kMarkerSize) return H::TooShort;
-            ho[k] = h_offsets[k], ht[k] = (uint32_t)tiles, hf[k] = (uint32_t)ftiles;
+            ho[k] = h_offsets[k], ht[k] = (uint32_t)tiles;
             tiles += (sz - H::kHeaderSize + kDecTB - 1) / kDecTB;
-            ftiles += (sz - H::kHeaderSize + kDtTB - 1) / kDtTB;
             if (tiles >= (1ull << 31)) return H::TooBig;
         }
-        ho[n_images] = h_offsets[n_images], ht[n_images] = (uint32_t)tiles, hf[n_images] = (uint32_t)ftiles;
+        ho[n_images] = h_offsets[n_images], ht[n_images] = (uint32_t)tiles;
         QB_CUDA(cudaMemcpyAsync(c->aux.p, ho, off_bytes + tf_bytes, cudaMemcpyHostToDevice, s));
         DecParams P{};
         P.qoi = d_qoi;
@@ -171,8 +142,7 @@ extern "C"
         P.out = d_out, P.out_stride = out_stride, P.n_pixels = n;
         P.width = desc->width, P.height = desc->height, P.target = tgt, P.flip = 0;
         P.n_images = n_images, P.n_tiles = (uint32_t)tiles;
-        const bool fast = use_fast_decode(c, h_offsets[n_images] - h_offsets[0], n * n_images, false);
-        return launch_decode(c, P, s, fast ? ftiles : 0, P.tile_first + n_images + 1);
+        return launch_decode(c, P, s);
     }
 
     int32_t qoipp_b200_stream_decode_host(qoipp_b200_ctx* c, qoipp_b200_state* st, const uint8_t* h_in, uint64_t in_size,
@@ -188,11 +158,11 @@ extern "C"
         // a call produces at most 62 pixels per input byte plus the pending run
         const uint64_t cap = std::min<uint64_t>(out_cap, (in_size * 62 + st->run) * ch);
         if (cap < ch) return 0;  // nothing to read and nothing pending
-        QB_CUDA(c->stage_in.reserve(in_size + 64));
-        QB_CUDA(c->stage_out.reserve(cap + 64));
-        QB_CUDA(c->state.reserve(sizeof(DecState)));
-        QB_CUDA(c->results.reserve(kCtrlBytes + sizeof(DecResult)));
         cudaStream_t s  = c->own_stream;
+        QB_CUDA(c->stage_in.reserve(in_size + 64, s));
+        QB_CUDA(c->stage_out.reserve(cap + 64, s));
+        QB_CUDA(c->state.reserve(sizeof(DecState), s));
+        QB_CUDA(c->results.reserve(kCtrlBytes + sizeof(DecResult), s));
         auto*        hs = reinterpret_cast<DecState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
         hs->prev = pack_px(st->prev), hs->run = st->run;
         for (int i = 0; i < 64; ++i) hs->table[i] = pack_px(st->seen[i]);

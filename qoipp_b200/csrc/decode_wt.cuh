@@ -1,0 +1,897 @@
+// decode_wt.cuh -- warp-autonomous tile decoder for sm_100a (+ the exact sequential loop it falls back on).
+//
+// Replaces the serial loop of the reference, impl::decode (source/simple.cpp:100-171).  A tile is kDecTB = 32 * kWtChunk
+// bytes of the chunk stream and belongs to ONE WARP: the warps of a CTA are independent persistent workers that draw
+// tiles from a ticket counter, nothing in the kernel needs __syncthreads.  A lane owns kWtChunk consecutive stream bytes
+// and walks its ops like the reference loop does -- cursor, delta accumulator, slot hash and pixel counter in registers.
+// What a lane cannot know at the start of its chunk is carried symbolically:
+//
+//   parse   an op's length depends on its tag byte only (simple.cpp:118-165): a chunk is a map {entry offset 0..4 -> exit
+//           offset}; maps compose across lanes (warp scan) and tiles (look-back 1).  No self-synchronisation is assumed.
+//           The same walk counts ops / pixels and finds the last OP_RGBA, so op ordinals, pixel offsets and the inherited
+//           alpha of every lane are known BEFORE the main walk (warp scans + look-back 2, pixels and alpha in one word).
+//   walk    ONE pass over the lane's ops writes a record per op, compact in stream order (op ordinal k):
+//             rec[k]  value relative to the op's base: absolute after a literal (OP_RGB / OP_RGBA), a delta otherwise
+//             base[k] the base node: ABS, the lane's entry node E_l (ops before the lane's first literal / OP_INDEX),
+//                     or the ordinal of the OP_INDEX op that roots the segment
+//             slot[k] table slot of the value (util::hash is linear mod 64, util.hpp:347-351: slots follow from the
+//                     literals by sums of 3dr+5dg+7db without knowing pixel values) | flags;  pix[k] pixel offset
+//   nodes   E_l and the OP_INDEX ops are the only nodes that point at other ops (E_l = the op before the lane's first,
+//           OP_INDEX = the last earlier op with the same slot, found by a backward search over slot[]).  Pointer jumping
+//           over these few nodes ends in ABS or in an entry of the state entering the tile (EXT: prev or a table slot).
+//   state   look-back 4: per tile a transfer function -- each of the 64 table slots and `prev` leaves the tile as a
+//           constant or as (incoming entry) + delta.  Only the entries a tile really reads are followed through the
+//           predecessors' words (lazy: an OP_INDEX-free tile reads `prev` alone).
+//   emit    data-parallel over the compact records (lane = op): value = rec[k] (+ rec[base]), verification, pixels stored
+//           straight to global memory (consecutive lanes = consecutive pixels), OP_RUN expanded by the whole warp.
+//
+// SPECULATION (unchanged from round 1).  The slot of an OP_RGB pixel needs its inherited alpha: assumed "alpha of the last
+// OP_RGBA before it, else 255" (+ alphas learned by earlier rounds), and an OP_INDEX is assumed to read a written slot.
+// Every tile VERIFIES both on the final values (OP_RGB: alpha equals its predecessor's; OP_INDEX: hash(value) == slot).
+// Verified => exact, by induction over op order.  A refuted tile records the alphas it saw; decode_finish_kernel re-decodes
+// from the first refuted tile on (up to kDecRounds rounds) and hands what still fails to the sequential loop.
+#pragma once
+
+#include "qb_common.cuh"
+
+namespace qb
+{
+    struct DecState {  // == StreamDecoder members (include/qoipp/stream.hpp:239-243), pixels packed
+        uint32_t prev;
+        uint32_t run;
+        uint32_t table[64];
+    };
+
+    constexpr int kDecRounds = 4;  // verification-driven retry rounds before the sequential loop takes over
+
+    struct DecResult {
+        uint32_t bad;   // round 0 refuted a speculation somewhere in this image
+        uint32_t path;  // retry rounds used; + 100 when the sequential loop produced (part of) the image
+        uint64_t pixels;
+        uint64_t processed;  // resumable decode: input bytes consumed / output bytes written / carry-out
+        uint64_t written;
+        uint32_t first_bad[kDecRounds + 1];  // per round: 0 = all verified, else 0xFFFFFFFF - first refuted tile
+        uint32_t pad[3];
+        DecState state;
+    };
+
+    struct DecControl {  // zeroed with the results before every decode
+        uint32_t tickets[kDecRounds + 1];  // tile tickets of round 0 and of the retry rounds
+        uint32_t any_bad[kDecRounds + 1];  // some image needs round r + 1
+        uint32_t pad[4];
+    };
+
+    struct DecParams {
+        const uint8_t*  qoi;
+        const uint64_t* offsets;     // [n_images + 1] device; null => single[]
+        const uint32_t* tile_first;  // [n_images + 1] device; null => single image
+        uint64_t        single[2];
+        uint8_t*        out;
+        uint64_t        out_stride;
+        uint64_t        n_pixels;
+        uint32_t        width, height, target, flip;
+        uint32_t        n_images, n_tiles, epoch, round;  // epoch = first epoch of this decode, round r uses epoch + r
+        DecResult*      results;
+        DecControl*     control;
+        uint64_t*       desc;
+        uint32_t*       fix;  // [n_tiles][kFixWords]: alpha learned at OP_RGB ops by earlier rounds
+    };
+
+#ifndef QB_WT_CHUNK
+#define QB_WT_CHUNK 28  // stream bytes per lane: an odd number of words keeps the lanes' chunk reads on different banks
+#endif
+#ifndef QB_WT_WARPS
+#define QB_WT_WARPS 4  // independent warp workers per CTA
+#endif
+#ifndef QB_WT_CTAS
+#define QB_WT_CTAS 5  // CTAs per SM the kernels are compiled for
+#endif
+    constexpr int kWtChunk = QB_WT_CHUNK, kDecTB = 32 * kWtChunk, kWtWarps = QB_WT_WARPS, kWtThreads = kWtWarps * 32;
+    static_assert(kWtChunk >= 8 && kWtChunk <= 28 && kWtChunk % 4 == 0, "op-start masks are 32 bits wide");
+
+    // node ids: op ordinals 0 .. kDecTB - 1, lane entry nodes, entries of the state entering the tile, "absolute"
+    constexpr unsigned kIdE = kDecTB, kIdExt = kDecTB + 32, kIdAbs = 0xFFFFu, kNoOp = 0xFFFFu, kNoPos = 0xFFFFu;
+    constexpr int      kWtNodes = kDecTB + 32 + 65;
+    constexpr unsigned kSlRgb = 0x40u, kSlIdx = 0x80u;  // flags beside the 6-bit slot
+
+    constexpr int kDecDescWords = 72;
+    constexpr int kDwParse = 0, kDwPixA = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
+    constexpr int kFixWords = 16, kFixMax = kFixWords - 1;  // word 0: count | decode tag << 8; entries: pos | alpha << 16
+
+    // parse map of a byte range: exit offset for each of the five possible entry offsets.  Entries 0..3 live in the
+    // bytes of `lo`, entry 4 in `hi`, so that composing two maps is two PRMT instructions.
+    struct Map {
+        unsigned lo, hi;
+    };
+    __device__ __forceinline__ Map map_identity() { return Map{ 0x03020100u, 4u }; }
+    __device__ __forceinline__ Map map_const(unsigned e) { return Map{ e * 0x01010101u, e }; }
+    __device__ __forceinline__ Map map_compose(const Map& f, const Map& g)  // f first, then g
+    {
+        const unsigned sel = (f.lo & 7u) | ((f.lo >> 4) & 0x70u) | ((f.lo >> 8) & 0x700u) | ((f.lo >> 12) & 0x7000u);
+        return Map{ __byte_perm(g.lo, g.hi, sel), __byte_perm(g.lo, g.hi, f.hi & 7u) & 0xFFu };
+    }
+    __device__ __forceinline__ unsigned map_at(const Map& f, unsigned e) { return e < 4u ? (f.lo >> (8u * e)) & 7u : f.hi & 7u; }
+    __device__ __forceinline__ unsigned map_pack(const Map& f)
+    {
+        return (f.lo & 7u) | ((f.lo >> 8) & 7u) << 3 | ((f.lo >> 16) & 7u) << 6 | ((f.lo >> 24) & 7u) << 9 | (f.hi & 7u) << 12;
+    }
+    __device__ __forceinline__ Map map_unpack(unsigned v)
+    {
+        return Map{ (v & 7u) | ((v >> 3) & 7u) << 8 | ((v >> 6) & 7u) << 16 | ((v >> 9) & 7u) << 24, (v >> 12) & 7u };
+    }
+
+    __device__ __forceinline__ unsigned op_length(unsigned tag)  // simple.cpp:118-165
+    {
+        return 1u + ((tag >> 6) == 2u) + 3u * (tag == kOpRgb) + 4u * (tag == kOpRgba);
+    }
+
+    // pixels before a tile (33 bits, saturating) and the alpha of the last OP_RGBA (0x100 | alpha, 0 = none so far)
+    struct PixA {
+        unsigned lo, hi, a;
+    };
+    constexpr uint64_t kPixSat = (1ull << 33) - 1;
+    __device__ __forceinline__ PixA pixa_comb(const PixA& x, const PixA& y)  // x happens before y
+    {
+        uint64_t s = ((uint64_t)x.hi << 32 | x.lo) + ((uint64_t)y.hi << 32 | y.lo);
+        if (s > kPixSat) s = kPixSat;
+        return PixA{ (unsigned)s, (unsigned)(s >> 32), (y.a & 0x100u) ? y.a : x.a };
+    }
+    __device__ __forceinline__ uint64_t pixa_pack(const PixA& x) { return ((uint64_t)x.hi << 32 | x.lo) | (uint64_t)(x.a & 0x1FFu) << 33; }
+    __device__ __forceinline__ PixA     pixa_unpack(uint64_t v) { return PixA{ (unsigned)v, (unsigned)(v >> 32) & 1u, (unsigned)(v >> 33) & 0x1FFu }; }
+
+    struct WtSmem {
+        alignas(16) unsigned char bytes[kDecTB + 48];  // tile bytes at [shift, shift + kDecTB + 8), zero padded
+        unsigned       rec[kWtNodes + 3];              // per node: value relative to its base (ops, E nodes, EXT entries)
+        unsigned short base[kDecTB + 32];              // per op / E node: base node id
+        unsigned short pix[kDecTB + 4];                // per op: tile-relative pixel offset (+ sentinel)
+        alignas(4) unsigned char slot[kDecTB + 4];     // per op: slot | flags
+        unsigned short lastk[64];                      // last op per slot
+        unsigned       fixe[kFixWords];                // learned alphas: pos | alpha << 16
+        unsigned       fails[kFixWords];               // OP_RGB ops refuted in this round: op ordinal | actual alpha << 16
+        unsigned char  hE[32];                         // slot of the value entering each lane's chunk
+        unsigned       nfail, fixn, fixn0, fix_dirty;
+    };
+
+    // store one pixel (target 3 or 4 bytes), optionally bottom-up rows (simple.cpp:401-408 done in place)
+    __device__ __forceinline__ void store_pixel(uint8_t* out, uint64_t pix, unsigned val, const DecParams& P)
+    {
+        if (P.flip) {
+            const uint64_t y = pix / P.width, x = pix - y * P.width;
+            pix = (uint64_t)(P.height - 1 - y) * P.width + x;
+        }
+        if (P.target == 4) {
+            uint8_t* d = out + pix * 4;
+            if ((reinterpret_cast<uintptr_t>(out) & 3u) == 0) *reinterpret_cast<unsigned*>(d) = val;
+            else d[0] = (uint8_t)val, d[1] = (uint8_t)(val >> 8), d[2] = (uint8_t)(val >> 16), d[3] = (uint8_t)(val >> 24);
+        } else {
+            uint8_t* d = out + pix * 3;
+            d[0] = (uint8_t)val, d[1] = (uint8_t)(val >> 8), d[2] = (uint8_t)(val >> 16);
+        }
+    }
+
+    __device__ __forceinline__ void locate_image(const DecParams& P, unsigned gt, unsigned& img, unsigned& t, unsigned& ntiles,
+                                                 const uint8_t*& stream, uint64_t& size)
+    {
+        if (P.tile_first == nullptr) {
+            img = 0, t = gt, ntiles = P.n_tiles;
+            stream = P.qoi + P.single[0], size = P.single[1] - P.single[0];
+            return;
+        }
+        unsigned lo = 0, hi = P.n_images;  // largest img with tile_first[img] <= gt
+        while (hi - lo > 1) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (__ldg(P.tile_first + mid) <= gt) lo = mid;
+            else hi = mid;
+        }
+        img    = lo;
+        const unsigned f = __ldg(P.tile_first + lo);
+        t = gt - f, ntiles = __ldg(P.tile_first + lo + 1) - f;
+        const uint64_t o0 = __ldg(P.offsets + lo);
+        stream = P.qoi + o0, size = __ldg(P.offsets + lo + 1) - o0;
+    }
+
+    // incoming value of state entry `e` (0..63 table slot, 64 prev) of tile `t`: follow the chain of transfer words
+    // through the predecessors until a constant (inclusive word) or the start of the stream.  `d_t` = descriptor of tile t.
+    __device__ __forceinline__ unsigned wt_resolve_entry(const uint64_t* d_t, unsigned t, unsigned e, const Epochs& ep)
+    {
+        unsigned acc = 0;
+        for (int p = (int)t - 1;; --p) {
+            if (p < 0) return add4((e == 64u || e == 53u) ? kStartPixel : 0u, acc);  // simple.cpp:103-108
+            const uint64_t wd = wait_word(d_t - (int64_t)(t - (unsigned)p) * kDecDescWords + kDwState + (int)e, ep, (unsigned)p);
+            const uint64_t pl = word_payload(wd);
+            if (raw_status(wd) == ST_INCL) return add4((unsigned)pl, acc);
+            acc = add4(acc, (unsigned)pl);
+            e   = (unsigned)(pl >> 32);
+        }
+    }
+
+    // one tile (global ticket `gticket`) of round `round`; one warp
+    __device__ __forceinline__ void wt_decode_tile(const DecParams& P, WtSmem& sm, unsigned round, unsigned gticket, unsigned img, unsigned t,
+                                                   unsigned ntiles, const uint8_t* stream, uint64_t size, unsigned fresh_from)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        [[maybe_unused]] const long long qb_t0 = QB_T0();
+        const uint64_t body_len = size - kHeader;  // every byte after the header is chunk data (simple.cpp:110-113)
+        const uint64_t tile_b0  = (uint64_t)t * kDecTB;
+        const unsigned limit    = (unsigned)(body_len - tile_b0 < (uint64_t)kDecTB ? body_len - tile_b0 : (uint64_t)kDecTB);
+        uint64_t*      desc     = P.desc + (uint64_t)gticket * kDecDescWords;
+        const unsigned epoch    = P.epoch + round;
+        const Epochs   ep{ epoch, P.epoch, fresh_from };
+        uint8_t*       out      = P.out + (uint64_t)img * P.out_stride;
+        const uint64_t N        = P.n_pixels;
+        DecResult*     res      = P.results + img;
+        uint32_t*      fix      = P.fix + (uint64_t)gticket * kFixWords;
+        auto word_of = [&](unsigned p, int which) { return desc - (int64_t)(t - p) * kDecDescWords + which; };
+
+        // ---- alpha values learned by earlier rounds for OP_RGB ops of this tile
+        if (lane < (unsigned)kFixWords) {
+            unsigned n = 0;
+            if (round > 0) {
+                const unsigned h = fix[0];
+                if ((h >> 8) == (P.epoch & 0xFFFFFFu)) n = min(h & 255u, (unsigned)kFixMax);
+                if (lane >= 1 && lane <= n) sm.fixe[lane - 1] = fix[lane];
+            }
+            if (lane == 0) sm.fixn = n, sm.fixn0 = n, sm.fix_dirty = 0, sm.nfail = 0;
+        }
+
+        // ---- stage the tile: 16-byte aligned vectors land at the same misalignment in shared memory
+        const uint8_t* src   = stream + kHeader + tile_b0;
+        const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+        {
+            const uint64_t avail = body_len - tile_b0;  // bytes of the stream from the tile start
+            const unsigned want  = (unsigned)(avail < (uint64_t)(kDecTB + 8) ? avail : (uint64_t)(kDecTB + 8));
+            const unsigned nvec  = (shift + want + 15u) >> 4;
+            const uint4*   vsrc  = reinterpret_cast<const uint4*>(src - shift);
+            for (unsigned c = lane; c < nvec; c += 32u) reinterpret_cast<uint4*>(sm.bytes)[c] = __ldg(vsrc + c);
+            __syncwarp();
+            for (unsigned b = shift + want + lane; b < (unsigned)kDecTB + 48u; b += 32u) sm.bytes[b] = 0;  // zero padding, simple.cpp:106
+            __syncwarp();
+        }
+        const unsigned char* B     = sm.bytes + shift;
+        const unsigned       fixn0 = sm.fixn0;
+        const unsigned       cbeg  = lane * kWtChunk;
+        const unsigned       cend  = min(cbeg + (unsigned)kWtChunk, limit);  // ops of this lane start below cend
+        QB_STAMP(desc, 68, 0, qb_t0);  // ticket + staging
+
+        // ================= look-back 1: parse map; counts along the path from entry offset 0 =================
+        unsigned M0 = 0, R0 = 0, X0 = 0, A0 = kNoPos;  // op starts / OP_RUN ops (bit = byte of the chunk), extra run pixels, last OP_RGBA
+        Map      mymap;
+        {
+            unsigned p = cbeg;
+            while (p < cend) {
+                const unsigned tag = B[p], bit = 1u << (p - cbeg);
+                M0 |= bit;
+                if (tag >= 0xC0u && tag < kOpRgb) R0 |= bit, X0 += tag & 63u;
+                if (tag == kOpRgba) A0 = p;
+                p += op_length(tag);
+            }
+            const unsigned cfull = cbeg + kWtChunk;
+            const unsigned exit0 = p > cfull ? p - cfull : 0u;
+            unsigned       win   = exit0;
+#pragma unroll 1
+            for (unsigned e = 1; e <= 4u; ++e) {  // a late entry usually falls into the path of entry 0 after an op or two
+                unsigned q = cbeg + e;
+                while (q < cend && !((M0 >> (q - cbeg)) & 1u)) q += op_length(B[q]);
+                win |= (q < cend ? exit0 : (q > cfull ? q - cfull : 0u)) << (3u * e);
+            }
+            mymap = map_unpack(win);
+        }
+        Map incl_map = mymap;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Map o = Map{ __shfl_up_sync(kFull, incl_map.lo, d), __shfl_up_sync(kFull, incl_map.hi, d) };
+            if ((int)lane >= d) incl_map = map_compose(o, incl_map);
+        }
+        Map excl_map = Map{ __shfl_up_sync(kFull, incl_map.lo, 1), __shfl_up_sync(kFull, incl_map.hi, 1) };
+        if (lane == 0) excl_map = map_identity();
+        const Map tile_map = Map{ __shfl_sync(kFull, incl_map.lo, 31), __shfl_sync(kFull, incl_map.hi, 31) };
+        unsigned  tile_entry;
+        {
+            if (lane == 0 && t > 0) st_word(desc + kDwParse, pack_word(map_pack(tile_map), ST_AGG, epoch));
+            const Map in = warp_lookback_lazy<Map>(
+                t, map_const(0), map_identity(),
+                [&](unsigned p, unsigned& st) {
+                    const uint64_t wd = ld_word(word_of(p, kDwParse));
+                    st                = ep.valid(wd, p) ? raw_status(wd) : (unsigned)ST_NONE;
+                    return map_unpack((unsigned)word_payload(wd));
+                },
+                [](const Map& a, const Map& b) { return map_compose(a, b); });
+            tile_entry = in.lo & 7u;  // `in` is constant: every chain ended in an inclusive word
+            if (lane == 0) st_word(desc + kDwParse, pack_word(map_pack(map_const(map_at(tile_map, tile_entry))), ST_INCL, epoch));
+        }
+        const unsigned my_entry = map_at(excl_map, tile_entry);
+        QB_STAMP(desc, 68, 1, qb_t0);  // parse + look-back 1
+
+        // ================= counts of the true path, look-back 2: pixels and inherited alpha =================
+        unsigned nops, npx_lane, a_sum;  // a_sum: 0x100 | alpha after this lane's last alpha setter, 0 = none
+        {
+            unsigned p = cbeg + my_entry, own = 0, ownx = 0, Apos = kNoPos, X;
+            while (p < cend && !((M0 >> (p - cbeg)) & 1u)) {  // until the path of entry 0 is met
+                const unsigned tag = B[p];
+                ++own;
+                if (tag >= 0xC0u && tag < kOpRgb) ownx += tag & 63u;
+                if (tag == kOpRgba) Apos = p;
+                p += op_length(tag);
+            }
+            if (p < cend) {
+                const unsigned rel = p - cbeg;
+                nops               = own + (unsigned)__popc(M0 >> rel);
+                unsigned xb        = 0;
+                for (unsigned bits = R0 & ((1u << rel) - 1u); bits; bits &= bits - 1u) xb += B[cbeg + (unsigned)__ffs((int)bits) - 1u] & 63u;
+                X = ownx + X0 - xb;
+                if (A0 != kNoPos && A0 >= p) Apos = A0;
+            } else {
+                nops = own, X = ownx;
+            }
+            npx_lane = nops + X;
+            a_sum    = Apos != kNoPos ? 0x100u | B[Apos + 4u] : 0u;
+            if (fixn0) {  // a learned alpha acts like an OP_RGBA from its op on
+                for (unsigned j = 0; j < fixn0; ++j) {
+                    const unsigned fp = sm.fixe[j] & 0xFFFFu;
+                    if (fp >= cbeg + my_entry && fp < cend && (Apos == kNoPos || fp > Apos)) Apos = fp, a_sum = 0x100u | ((sm.fixe[j] >> 16) & 255u);
+                }
+            }
+        }
+        unsigned opbase, pixbase, n_ops, n_pix, alpha_lane;
+        uint64_t pix_base;
+        {
+            const unsigned mine = npx_lane | nops << 16;
+            unsigned       inc  = mine, ai = a_sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(kFull, inc, d), oa = __shfl_up_sync(kFull, ai, d);
+                if ((int)lane >= d) {
+                    inc += o;
+                    if (!(ai & 0x100u)) ai = oa;
+                }
+            }
+            const unsigned tot = __shfl_sync(kFull, inc, 31), atot = __shfl_sync(kFull, ai, 31);
+            unsigned       aex = __shfl_up_sync(kFull, ai, 1);
+            if (lane == 0) aex = 0;
+            opbase = (inc - mine) >> 16, pixbase = (inc - mine) & 0xFFFFu;
+            n_ops = tot >> 16, n_pix = tot & 0xFFFFu;
+            const PixA agg{ n_pix, 0u, atot };
+            if (lane == 0 && t > 0) st_word(desc + kDwPixA, pack_word(pixa_pack(agg), ST_AGG, epoch));
+            const PixA in = warp_lookback_lazy<PixA>(
+                t, PixA{ 0u, 0u, 0x1FFu }, PixA{ 0u, 0u, 0u },
+                [&](unsigned p, unsigned& st) {
+                    const uint64_t wd = ld_word(word_of(p, kDwPixA));
+                    st                = ep.valid(wd, p) ? raw_status(wd) : (unsigned)ST_NONE;
+                    return pixa_unpack(word_payload(wd));
+                },
+                [](const PixA& a, const PixA& b) { return pixa_comb(a, b); });
+            if (lane == 0) st_word(desc + kDwPixA, pack_word(pixa_pack(pixa_comb(in, agg)), ST_INCL, epoch));
+            pix_base   = (uint64_t)in.hi << 32 | in.lo;
+            alpha_lane = ((aex & 0x100u) ? aex : in.a) & 255u;
+        }
+        QB_STAMP(desc, 69, 0, qb_t0);  // counts + look-back 2
+
+        // ================= the walk: one record per op =================
+        unsigned       idxm = 0;  // OP_INDEX ops of this lane (bit = op number within the lane)
+        unsigned       exit_bid, exit_h;
+        const unsigned* S32 = reinterpret_cast<const unsigned*>(sm.bytes);
+        {
+            unsigned p = cbeg + my_entry, k = opbase, px = pixbase, j = 0;
+            unsigned acc = 0, bid = kIdE + lane, h = 0, alpha = alpha_lane;
+            while (p < cend) {
+                const unsigned a  = shift + p;
+                const unsigned x  = __funnelshift_r(S32[a >> 2], S32[(a >> 2) + 1u], (a & 3u) * 8u);  // the op's first four bytes
+                const unsigned tag = x & 0xFFu;
+                unsigned       len = 1, npx = 1, fl = 0;
+                if (tag >= kOpRgb) {  // simple.cpp:119-129; OP_RGB keeps the alpha: speculated here, verified in the emit pass
+                    if (tag == kOpRgba) alpha = sm.bytes[a + 4u];
+                    else {
+                        fl = kSlRgb;
+                        if (fixn0)
+                            for (unsigned f = 0; f < fixn0; ++f)
+                                if ((sm.fixe[f] & 0xFFFFu) == p) alpha = (sm.fixe[f] >> 16) & 255u;
+                    }
+                    acc = (x >> 8) | alpha << 24, bid = kIdAbs, h = slot_of(acc), len = 4u + (tag & 1u);
+                } else {
+                    const unsigned hi = tag >> 6;
+                    if (hi == 1u) {  // simple.cpp:136-144
+                        const unsigned d = add4(((tag >> 4) & 3u) | ((tag >> 2) & 3u) << 8 | (tag & 3u) << 16, 0x00FEFEFEu);
+                        acc = add4(acc, d), h += __dp4a(d, 0x00070503u, 0u);
+                    } else if (hi == 2u) {  // simple.cpp:145-155
+                        const unsigned rb = (x >> 8) & 0xFFu, vg = (tag + 0x60u) & 0xFFu;  // dg = (tag & 63) - 32
+                        const unsigned d  = ((vg + (rb >> 4) + 248u) & 255u) | vg << 8 | ((vg + (rb & 15u) + 248u) & 255u) << 16;
+                        acc = add4(acc, d), h += __dp4a(d, 0x00070503u, 0u), len = 2;
+                    } else if (hi == 0u) {  // simple.cpp:132-135: the value is found by the search below
+                        acc = 0, bid = k, h = tag, fl = kSlIdx, idxm |= 1u << j;
+                    } else {
+                        npx = (tag & 63u) + 1u;  // simple.cpp:156-163: repeats the record of the previous op
+                    }
+                }
+                sm.rec[k]  = acc;
+                sm.base[k] = (unsigned short)bid;
+                sm.slot[k] = (unsigned char)((h & 63u) | fl);
+                sm.pix[k]  = (unsigned short)px;
+                px += npx, ++k, ++j, p += len;
+            }
+            exit_bid = bid, exit_h = h & 63u;
+        }
+        // the lane's entry node: the op before its first one (or the value entering the tile)
+        sm.base[kIdE + lane] = (unsigned short)(opbase ? opbase - 1u : kIdExt + 64u);
+        sm.rec[kIdE + lane]  = 0;
+        sm.lastk[lane] = (unsigned short)kNoOp, sm.lastk[lane + 32] = (unsigned short)kNoOp;
+        if (lane == 0) sm.pix[n_ops] = (unsigned short)n_pix;
+        QB_STAMP(desc, 69, 1, qb_t0);  // walk
+
+        // ================= look-back 3: slot of the value entering the tile / every lane =================
+        {
+            const bool     rooted = exit_bid != kIdE + lane;  // a literal or an OP_INDEX made the slot absolute
+            const unsigned mine   = exit_h | (rooted ? 64u : 0u);
+            auto comb = [](unsigned a, unsigned b) { return (b & 64u) ? b : ((a & 64u) | ((a + b) & 63u)); };  // a before b
+            unsigned inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned o = __shfl_up_sync(kFull, inc, d);
+                if ((int)lane >= d) inc = comb(o, inc);
+            }
+            const unsigned tot = __shfl_sync(kFull, inc, 31);
+            unsigned       ex  = __shfl_up_sync(kFull, inc, 1);
+            if (lane == 0) ex = 0;
+            if (lane == 0 && t > 0) st_word(desc + kDwSlot, pack_word(tot, (tot & 64u) ? ST_INCL : ST_AGG, epoch));
+            const unsigned in = warp_lookback_lazy<unsigned>(
+                t, 64u | 53u, 0u,  // {0,0,0,255}: slot 53 (simple.cpp:108)
+                [&](unsigned p, unsigned& st) {
+                    if (p < ep.fresh_from) {  // a tile finished by an earlier round: take the slot of its actual last pixel
+                        const uint64_t wd = ld_word(word_of(p, kDwState + 64));
+                        st                = (ep.valid(wd, p) && raw_status(wd) == ST_INCL) ? (unsigned)ST_INCL : (unsigned)ST_NONE;
+                        return 64u | slot_of((unsigned)word_payload(wd));
+                    }
+                    const uint64_t wd = ld_word(word_of(p, kDwSlot));
+                    st                = ep.valid(wd, p) ? raw_status(wd) : (unsigned)ST_NONE;
+                    return (unsigned)word_payload(wd);
+                },
+                comb);
+            if (lane == 0 && (t == 0 || !(tot & 64u))) st_word(desc + kDwSlot, pack_word(comb(in, tot), ST_INCL, epoch));
+            sm.hE[lane] = (unsigned char)((ex & 64u) ? ex & 63u : (in + ex) & 63u);
+        }
+        __syncwarp();
+
+        // ================= absolute slots, last op per slot (lane = op) =================
+        for (unsigned kb = 0; kb < n_ops; kb += 32u) {
+            const unsigned k     = kb + lane;
+            const bool     valid = k < n_ops;
+            unsigned       s     = 64u + lane;
+            if (valid) {
+                const unsigned s8 = sm.slot[k], b = sm.base[k];
+                s = s8 & 63u;
+                if (b >= kIdE && b < kIdExt) {  // before the lane's first root: the walk knew the slot relative to the lane's entry
+                    s          = (s + sm.hE[b - kIdE]) & 63u;
+                    sm.slot[k] = (unsigned char)(s | (s8 & 0xC0u));
+                }
+            }
+            const unsigned m = __match_any_sync(kFull, s);
+            if (valid && (m & lanemask_gt(lane)) == 0) sm.lastk[s] = (unsigned short)k;
+            __syncwarp();
+        }
+        QB_STAMP(desc, 70, 0, qb_t0);  // slots + last writers
+
+        // ================= OP_INDEX: the last earlier op with the same slot =================
+        unsigned need_lo = 0, need_hi = 0;  // table entries of the state entering the tile that are read
+        if (__ballot_sync(kFull, idxm != 0)) {
+            const unsigned* W = reinterpret_cast<const unsigned*>(sm.slot);
+            for (unsigned bits = idxm; bits; bits &= bits - 1u) {
+                const unsigned q = opbase + (unsigned)__ffs((int)bits) - 1u, s = sm.slot[q] & 63u;
+                const unsigned pat = s * 0x01010101u;
+                unsigned       found = kNoOp;
+                unsigned       keep  = (1u << (8u * (q & 3u))) - 1u;  // first word: only the ops before q
+                for (int wi = (int)(q >> 2); wi >= 0; --wi) {
+                    const unsigned x = (W[wi] & 0x3F3F3F3Fu) ^ pat;            // bytes 0..0x3F, zero where the slot matches
+                    const unsigned m = (0x40404040u - x) & 0x40404040u & keep;  // no borrow crosses a byte
+                    if (m) {
+                        found = (unsigned)wi * 4u + ((31u - (unsigned)__clz((int)m)) >> 3);
+                        break;
+                    }
+                    keep = 0xFFFFFFFFu;
+                }
+                if (found != kNoOp) sm.base[q] = (unsigned short)found;
+                else {
+                    sm.base[q] = (unsigned short)(kIdExt + s);
+                    if (s < 32u) need_lo |= 1u << s;
+                    else need_hi |= 1u << (s - 32u);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ================= pointer jumping over the entry nodes and the OP_INDEX ops =================
+        {
+            const unsigned maxJ = __reduce_max_sync(kFull, 1u + (unsigned)__popc(idxm));
+            for (;;) {
+                bool     changed = false;
+                unsigned bits    = idxm;
+                for (unsigned i = 0; i < maxJ; ++i) {
+                    unsigned x = kNoOp;
+                    if (i == 0) x = kIdE + lane;
+                    else if (bits) x = opbase + (unsigned)__ffs((int)bits) - 1u, bits &= bits - 1u;
+                    unsigned nb = 0, nr = 0;
+                    bool     upd = false;
+                    if (x != kNoOp) {
+                        const unsigned b = sm.base[x];
+                        if (b < kIdExt) nb = sm.base[b], nr = add4(sm.rec[x], sm.rec[b]), upd = true;
+                    }
+                    __syncwarp();  // every lane has read its target before any node changes
+                    if (upd) sm.base[x] = (unsigned short)nb, sm.rec[x] = nr, changed = true;
+                    __syncwarp();
+                }
+                if (!__ballot_sync(kFull, changed)) break;
+            }
+            // entries of the incoming state the nodes end in
+            unsigned bits = idxm;
+            for (unsigned i = 0; i <= (unsigned)__popc(idxm); ++i) {
+                unsigned x = kIdE + lane;
+                if (i) x = opbase + (unsigned)__ffs((int)bits) - 1u, bits &= bits - 1u;
+                const unsigned b = sm.base[x];
+                if (b != kIdAbs && b < kIdExt + 64u) {
+                    const unsigned e = b - kIdExt;
+                    if (e < 32u) need_lo |= 1u << e;
+                    else need_hi |= 1u << (e - 32u);
+                }
+            }
+        }
+        QB_STAMP(desc, 70, 1, qb_t0);  // index search + jumping
+
+        // ================= the tile's transfer function: entries it can state now =================
+        // entry e = lane, lane + 32 (table slots) and, in lane 0, 64 (prev)
+        unsigned pub_ref[3], pub_add[3];  // ref: 0..64 = incoming entry, 65 = constant (published inclusive already)
+        const bool tail_fill = t == ntiles - 1 && pix_base + n_pix < N;  // the stream ends before the image does
+#pragma unroll
+        for (int hh = 0; hh < 3; ++hh) {
+            const unsigned e = lane + 32u * hh;
+            pub_ref[hh] = 66u, pub_add[hh] = 0;
+            if (e > 64u) continue;
+            const unsigned k = e < 64u ? sm.lastk[e] : (n_ops ? n_ops - 1u : kNoOp);
+            unsigned       ref = e, add = 0;
+            if (k != kNoOp) {
+                unsigned b = sm.base[k];
+                add        = sm.rec[k];
+                if (b < kIdExt) add = add4(add, sm.rec[b]), b = sm.base[b];  // one hop: entry nodes and OP_INDEX ops are final
+                ref = b == kIdAbs ? 65u : b - kIdExt;
+            }
+            pub_ref[hh] = ref, pub_add[hh] = add;
+            if (ref == 65u) st_word(desc + kDwState + e, pack_word(add, ST_INCL, epoch));
+            else st_word(desc + kDwState + e, pack_word((uint64_t)ref << 32 | add, ST_AGG, epoch));
+            if (k != kNoOp && ref < 64u) {  // an entry this tile writes from an incoming one: resolve it, publish it inclusive below
+                if (ref < 32u) need_lo |= 1u << ref;
+                else need_hi |= 1u << (ref - 32u);
+            }
+        }
+        if (tail_fill) need_lo |= 1u;  // the zero padding decodes as OP_INDEX 0
+
+        // ================= look-back 4: the entries of the incoming state that are read =================
+        need_lo = __reduce_or_sync(kFull, need_lo), need_hi = __reduce_or_sync(kFull, need_hi);
+        if ((need_lo >> lane) & 1u) sm.rec[kIdExt + lane] = wt_resolve_entry(desc, t, lane, ep);
+        if ((need_hi >> lane) & 1u) sm.rec[kIdExt + 32u + lane] = wt_resolve_entry(desc, t, lane + 32u, ep);
+        if (lane == 0) sm.rec[kIdExt + 64u] = wt_resolve_entry(desc, t, 64u, ep);  // prev: nearly every tile reads it
+        __syncwarp();
+        const unsigned prev_in = sm.rec[kIdExt + 64u];
+        // now-known entries become inclusive words, so later tiles stop here
+#pragma unroll
+        for (int hh = 0; hh < 3; ++hh) {
+            const unsigned e = lane + 32u * hh;
+            if (pub_ref[hh] <= 64u) {
+                const bool known = pub_ref[hh] == 64u || ((pub_ref[hh] < 32u ? need_lo >> pub_ref[hh] : need_hi >> (pub_ref[hh] - 32u)) & 1u);
+                if (known) {
+                    pub_add[hh] = add4(pub_add[hh], sm.rec[kIdExt + pub_ref[hh]]);
+                    st_word(desc + kDwState + e, pack_word(pub_add[hh], ST_INCL, epoch));
+                }
+            }
+        }
+        // entry nodes and OP_INDEX ops become absolute
+        {
+            unsigned bits = idxm;
+            for (unsigned i = 0; i <= (unsigned)__popc(idxm); ++i) {
+                unsigned x = kIdE + lane;
+                if (i) x = opbase + (unsigned)__ffs((int)bits) - 1u, bits &= bits - 1u;
+                const unsigned b = sm.base[x];
+                if (b != kIdAbs) sm.rec[x] = add4(sm.rec[x], sm.rec[b]), sm.base[x] = (unsigned short)kIdAbs;
+            }
+        }
+        __syncwarp();
+        QB_STAMP(desc, 71, 0, qb_t0);  // state look-back
+
+        // ================= emit: values, verification, pixels (lane = op) =================
+        bool     bad   = false;
+        unsigned carry = prev_in;  // value of the op before this step's first one
+        for (unsigned kb = 0; kb < n_ops; kb += 32u) {
+            const unsigned k     = kb + lane;
+            const bool     valid = k < n_ops;
+            unsigned       v = 0, sl = 0, p0 = 0, np = 0;
+            if (valid) {
+                v                = sm.rec[k];
+                const unsigned b = sm.base[k];
+                if (b != kIdAbs) v = add4(v, sm.rec[b]);
+                sl = sm.slot[k], p0 = sm.pix[k], np = sm.pix[k + 1u] - p0;
+            }
+            unsigned up = __shfl_up_sync(kFull, v, 1);
+            if (lane == 0) up = carry;
+            carry = __shfl_sync(kFull, v, 31);
+            const bool live = valid && pix_base + p0 < N;  // ops past the image are never executed by the reference
+            if (live) {
+                if ((sl & kSlRgb) && (v >> 24) != (up >> 24)) {  // simple.cpp:119-123: the alpha is inherited from the previous pixel
+                    bad              = true;
+                    const unsigned f = atomicAdd(&sm.nfail, 1u);
+                    if (f < (unsigned)kFixMax) sm.fails[f] = k | (up >> 24) << 16;
+                }
+                if ((sl & kSlIdx) && slot_of(v) != (sl & 63u)) bad = true;  // a never-written (or mis-predicted) slot was read
+                store_pixel(out, pix_base + p0, v, P);
+            }
+            unsigned runs = __ballot_sync(kFull, live && np > 1u);  // OP_RUN pixels are written by the whole warp (clamped, simple.cpp:158)
+            while (runs) {
+                const int src = __ffs((int)runs) - 1;
+                runs &= runs - 1u;
+                const unsigned rp = __shfl_sync(kFull, p0, src), rn = __shfl_sync(kFull, np, src), rv = __shfl_sync(kFull, v, src);
+                for (unsigned j = 1u + lane; j < rn && pix_base + rp + j < N; j += 32u) store_pixel(out, pix_base + rp + j, rv, P);
+            }
+        }
+        // a refuted tile makes the image eligible for the next round, from the first such tile on
+        if (__ballot_sync(kFull, bad)) {
+            if (lane == 0) {
+                if (round == 0) atomicOr(&res->bad, 1u);
+                atomicMax(&res->first_bad[round], 0xFFFFFFFFu - t);
+                P.control->any_bad[round] = 1;
+            }
+            __syncwarp();
+            // remember the alpha seen at each refuted OP_RGB for the next round (exact if everything before it was exact)
+            const unsigned nf = min(sm.nfail, (unsigned)kFixMax);
+            for (unsigned f = 0; f < nf; ++f) {
+                const unsigned k = sm.fails[f] & 0xFFFFu, actual = sm.fails[f] >> 16;
+                if (k >= opbase && k < opbase + nops) {  // the owning lane walks to the op's byte position
+                    unsigned p = cbeg + my_entry;
+                    for (unsigned i = opbase; i < k; ++i) p += op_length(B[p]);
+                    unsigned j = 0;
+                    for (; j < sm.fixn; ++j)
+                        if ((sm.fixe[j] & 0xFFFFu) == p) break;
+                    if (j < (unsigned)kFixMax) {
+                        sm.fixe[j] = p | actual << 16;
+                        if (j == sm.fixn) sm.fixn = j + 1u;
+                        sm.fix_dirty = 1;
+                    }
+                }
+                __syncwarp();
+            }
+            if (sm.fix_dirty && lane < (unsigned)kFixWords) {
+                const unsigned n = min(sm.fixn, (unsigned)kFixMax);
+                fix[lane] = lane == 0 ? (n | (P.epoch & 0xFFFFFFu) << 8) : (lane <= n ? sm.fixe[lane - 1] : 0u);
+            }
+        }
+        QB_STAMP(desc, 71, 1, qb_t0);  // emit
+
+        // ---- the stream ended before the image: the zero padding decodes as INDEX 0 forever (simple.cpp:106,132-135)
+        if (t == ntiles - 1) {
+            const uint64_t have = pix_base + n_pix;
+            if (lane == 0) res->pixels = have < N ? have : N;
+            if (tail_fill) {
+                unsigned fill = sm.rec[kIdExt + 0u];  // table[0] after this tile
+                const unsigned k0 = sm.lastk[0];
+                if (k0 != kNoOp) {
+                    fill             = sm.rec[k0];
+                    const unsigned b = sm.base[k0];
+                    if (b != kIdAbs) fill = add4(fill, sm.rec[b]);
+                }
+                if (lane == 0 && slot_of(fill) != 0) {  // cannot happen while the table invariant holds; be safe
+                    atomicMax(&res->first_bad[round], 0xFFFFFFFFu - t);
+                    P.control->any_bad[round] = 1;
+                }
+                for (uint64_t pix = have + lane; pix < N; pix += 32u) store_pixel(out, pix, fill, P);
+            }
+        }
+        __syncwarp();
+    }
+
+    // round 0: persistent, independent warps draw tiles from a ticket counter in start order, so every tile a running warp
+    // waits for is held by a warp that is running too or done
+    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_wt_kernel(const DecParams P)
+    {
+        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM)[threadIdx.x >> 5];
+        const unsigned lane = threadIdx.x & 31u;
+        for (;;) {
+            unsigned x = 0;
+            if (lane == 0) x = atomicAdd(&P.control->tickets[0], 1u);
+            x = __shfl_sync(kFull, x, 0);
+            if (x >= P.n_tiles) break;
+            unsigned       img, t, ntiles;
+            const uint8_t* stream;
+            uint64_t       size;
+            locate_image(P, x, img, t, ntiles, stream, size);
+            wt_decode_tile(P, sm, 0u, x, img, t, ntiles, stream, size, 0u);
+        }
+    }
+
+    // =====================================================================================================
+    // Exact sequential decoder: the reference loop (simple.cpp:100-171, stream.cpp:312-447) with one decoding lane per
+    // image; the other 31 lanes stage input and output through shared memory.  Runs for images the retry rounds could not
+    // verify (mode 0), and for the resumable entry point (mode 1).
+    // =====================================================================================================
+    struct SerialParams {
+        DecParams       d;
+        uint32_t        mode;      // 0 = redo images flagged bad; 1 = resumable decode of one buffer
+        const DecState* init;      // mode 1 carry-in
+        uint64_t        in_size;   // mode 1: bytes available (no header), out capacity in bytes is d.out_stride
+    };
+
+    constexpr int kSerIn = 4096, kSerOut = 1024;
+    struct SerialSmem {
+        unsigned char in[kSerIn + 16];
+        unsigned      px[kSerOut];
+        unsigned      table[64];
+        unsigned      ctl[8];
+    };
+
+    // one warp; `img` selects the image (mode 0) -- called by decode_finish_kernel and decode_serial_kernel
+    __device__ __forceinline__ void decode_serial_body(const SerialParams& S, SerialSmem& sm, unsigned img)
+    {
+        const DecParams&      P    = S.d;
+        const unsigned        lane = threadIdx.x & 31u;
+        DecResult*            res  = P.results + img;
+        unsigned restart = 0;  // mode 0: first tile to decode again (the tiles before it verified in some round)
+        if (S.mode == 0) {
+            unsigned rounds = 0;
+            for (int r = 0; r < kDecRounds; ++r)
+                if (res->first_bad[r]) rounds = r + 1;
+            const unsigned fb = res->first_bad[kDecRounds];
+            __syncwarp();
+            if (lane == 0) res->path = rounds + (fb ? 100u : 0u);
+            if (fb == 0) return;
+            restart = 0xFFFFFFFFu - fb;
+        }
+
+        const uint8_t* stream;
+        uint64_t       size;
+        unsigned       first_tile = 0;
+        if (P.tile_first == nullptr) stream = P.qoi + P.single[0], size = P.single[1] - P.single[0];
+        else stream = P.qoi + P.offsets[img], size = P.offsets[img + 1] - P.offsets[img], first_tile = P.tile_first[img];
+        uint8_t*       out   = P.out + (uint64_t)img * (S.mode == 0 ? P.out_stride : 0);
+        const uint8_t* body  = S.mode == 0 ? stream + kHeader : stream;
+        const uint64_t blen  = S.mode == 0 ? size - kHeader : S.in_size;
+        const uint64_t room  = S.mode == 0 ? P.n_pixels : P.out_stride / P.target;  // pixels that may be produced
+
+        sm.table[lane] = 0, sm.table[lane + 32] = 0;
+        __syncwarp();
+        unsigned prev = kStartPixel, run = 0;
+        uint64_t pos = 0, px = 0;  // consumed input bytes, produced pixels
+        if (S.mode == 1) {
+            prev = S.init->prev, run = S.init->run;
+            sm.table[lane] = S.init->table[lane], sm.table[lane + 32] = S.init->table[lane + 32];
+        } else if (restart > 0) {
+            // resume behind the last verified tile: the decoder state there follows from the verified tiles' transfer words
+            const uint64_t* d_r = P.desc + (uint64_t)(first_tile + restart) * kDecDescWords;  // descriptor of tile `restart`
+            const uint64_t* d   = d_r - kDecDescWords;
+            const Epochs    ep{ P.epoch + (unsigned)kDecRounds + 1u, P.epoch, restart };  // any epoch of this decode is final below `restart`
+            pos                 = (uint64_t)restart * kDecTB + (word_payload(d[kDwParse]) & 7u);
+            px                  = word_payload(d[kDwPixA]) & kPixSat;
+            prev                = wt_resolve_entry(d_r, restart, 64u, ep);
+            sm.table[lane] = wt_resolve_entry(d_r, restart, lane, ep), sm.table[lane + 32] = wt_resolve_entry(d_r, restart, lane + 32u, ep);
+            prev = __shfl_sync(kFull, prev, 0);
+        } else if (lane == 0) {
+            sm.table[53] = kStartPixel;  // simple.cpp:108
+        }
+        __syncwarp();
+
+        bool     stop = false;
+        while (!stop && px < room) {
+            // stage kSerIn bytes from `pos` (zero padded past the end: simple.cpp:106)
+            for (unsigned b = lane; b < kSerIn + 16; b += 32) sm.in[b] = pos + b < blen ? body[pos + b] : 0;
+            __syncwarp();
+            if (lane == 0) {
+                // The next bytes of the stream live in a 64-bit register window refilled from prefetched words, so the
+                // tag -> length -> next tag chain never waits for shared memory.
+                const unsigned* in32 = reinterpret_cast<const unsigned*>(sm.in);
+                uint64_t        win  = (uint64_t)in32[0] | (uint64_t)in32[1] << 32;
+                unsigned        avail = 8, wnext = 4, n0 = in32[2], n1 = in32[3];
+                unsigned        ip = 0, op = 0;
+                while (op < kSerOut && px + op < room) {
+                    if (run) {  // pending run (stream.cpp:335-339)
+                        --run, sm.px[op++] = prev;
+                        continue;
+                    }
+                    if (ip >= kSerIn) break;
+                    const unsigned tag = (unsigned)win & 0xFFu, len = op_length(tag);
+                    if (S.mode == 1 && pos + ip + len > blen) { stop = true; break; }  // stream.cpp:341-392: incomplete op is not consumed
+                    const unsigned pay = (unsigned)(win >> 8);  // the four bytes after the tag
+                    unsigned       cur = prev;
+                    bool           is_run = false;
+                    if (tag == kOpRgb) cur = (pay & 0xFFFFFFu) | (prev & 0xFF000000u);  // simple.cpp:119-123
+                    else if (tag == kOpRgba) cur = pay;
+                    else if ((tag >> 6) == 0) cur = sm.table[tag & 63u];
+                    else if ((tag >> 6) == 1)
+                        cur = add4(prev, add4(((tag >> 4) & 3u) | ((tag >> 2) & 3u) << 8 | (tag & 3u) << 16, 0x00FEFEFEu));
+                    else if ((tag >> 6) == 2) {
+                        const unsigned rb = pay & 0xFFu, vg = ((tag & 63u) + 224u) & 255u;
+                        cur = add4(prev, ((vg + (rb >> 4) + 248u) & 255u) | vg << 8 | ((vg + (rb & 15u) + 248u) & 255u) << 16);
+                    } else {
+                        run = tag & 63u, is_run = true;  // RUN: one pixel now, the rest pending (simple.cpp:156-163)
+                    }
+                    ip += len, avail -= len;
+                    win = len == 8 ? 0 : win >> (8u * len);
+                    while (avail <= 4) {
+                        win |= (uint64_t)n0 << (8u * avail);
+                        avail += 4, n0 = n1, n1 = in32[wnext < (kSerIn + 16) / 4 ? wnext : 0];
+                        ++wnext;
+                    }
+                    sm.px[op++] = cur;
+                    if (!is_run) sm.table[slot_of(cur)] = cur;  // simple.cpp:169
+                    prev = cur;
+                }
+                sm.ctl[0] = ip, sm.ctl[1] = op, sm.ctl[2] = stop;
+            }
+            __syncwarp();
+            const unsigned ip = sm.ctl[0], op = sm.ctl[1];
+            stop = sm.ctl[2] != 0;
+            for (unsigned j = lane; j < op; j += 32) store_pixel(out, px + j, sm.px[j], P);
+            __syncwarp();
+            pos += ip, px += op;
+            if (ip == 0 && op == 0) break;
+        }
+        if (S.mode == 0) {
+            if (lane == 0) res->pixels = px;
+            return;
+        }
+        // mode 1 carry-out.  A run that is still pending when the input of mode 0 ends is dropped by the clamp
+        // (simple.cpp:158); in mode 1 it stays in the state (stream.cpp:405-409).
+        prev = __shfl_sync(kFull, prev, 0), run = __shfl_sync(kFull, run, 0);
+        res->state.table[lane] = sm.table[lane], res->state.table[lane + 32] = sm.table[lane + 32];
+        if (lane == 0) {
+            res->state.prev = prev, res->state.run = run;
+            res->processed = pos, res->written = px * P.target, res->path = 1;
+        }
+    }
+
+    // resumable decode (mode 1): one warp
+    __global__ void __launch_bounds__(32) decode_serial_kernel(const SerialParams S)
+    {
+        decode_serial_body(S, *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM), 0u);
+    }
+
+    constexpr size_t kWtSmemBytes = sizeof(WtSmem) * kWtWarps > sizeof(SerialSmem) ? sizeof(WtSmem) * kWtWarps : sizeof(SerialSmem);
+
+    // Everything after round 0, in ONE cooperative launch of co-resident persistent CTAs (so that an image that
+    // verified costs a single empty launch): rounds 1..kDecRounds re-decode, per image, the tiles from the first refuted
+    // one on with the alphas learned by the round before (grid-wide barrier between rounds); what still fails after the
+    // last round is decoded by the sequential loop, one warp per image, resuming behind the last verified tile.
+    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_finish_kernel(const DecParams P)
+    {
+        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM)[threadIdx.x >> 5];
+        const unsigned lane = threadIdx.x & 31u;
+        for (unsigned round = 1; round <= (unsigned)kDecRounds; ++round) {
+            if (P.control->any_bad[round - 1] == 0) break;  // same value in every CTA: final since the last barrier
+            for (;;) {
+                unsigned x = 0;
+                if (lane == 0) x = atomicAdd(&P.control->tickets[round], 1u);
+                x = __shfl_sync(kFull, x, 0);
+                if (x >= P.n_tiles) break;
+                unsigned       img, t, ntiles;
+                const uint8_t* stream;
+                uint64_t       size;
+                locate_image(P, x, img, t, ntiles, stream, size);
+                const unsigned fb = P.results[img].first_bad[round - 1];
+                if (fb == 0 || t < 0xFFFFFFFFu - fb) continue;  // image verified, or a tile before the first refuted one: final
+                wt_decode_tile(P, sm, round, x, img, t, ntiles, stream, size, 0xFFFFFFFFu - fb);
+            }
+            QB_GRID_SYNC();
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            SerialParams S{};
+            S.d = P, S.mode = 0;
+            for (unsigned img = blockIdx.x; img < P.n_images; img += gridDim.x)
+                decode_serial_body(S, *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM), img);
+        }
+    }
+
+#ifndef QB_EMU
+    inline cudaError_t dec_set_attrs()
+    {
+        cudaError_t e = cudaFuncSetAttribute(decode_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(decode_wt_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+#endif
+}  // namespace qb

@@ -3,8 +3,7 @@
 // CUDA device and fails with a negative cudaError_t (or BadAlloc) otherwise.
 #include "../../include/qoipp_b200.h"
 
-#include "decode_kernel.cuh"
-#include "decode_ts.cuh"
+#include "decode_wt.cuh"
 #include "encode_kernel.cuh"
 #include "encode_ts.cuh"
 #include "host_util.hpp"
@@ -49,17 +48,23 @@ namespace
     struct DevBuf {
         void*  p   = nullptr;
         size_t cap = 0;
-        // grow-only; contents are NOT preserved.  `zero` clears the new allocation.
-        cudaError_t reserve(size_t n, bool zero = false)
+        // grow-only; contents are NOT preserved.  `zero` clears the new allocation, ordered on the call's stream `s`
+        // (the kernels that read it are launched on `s`; a plain cudaMemset would run on the legacy default stream,
+        // unordered against a non-blocking stream).  Growing waits for `s` first: an earlier launch may still use the old buffer.
+        cudaError_t reserve(size_t n, cudaStream_t s, bool zero = false)
         {
             if (n <= cap) return cudaSuccess;
-            if (p) cudaFree(p);
+            if (p) {
+                cudaError_t e = cudaStreamSynchronize(s);
+                if (e != cudaSuccess) return e;
+                cudaFree(p);
+            }
             p = nullptr, cap = 0;
             size_t      want = std::max<size_t>(n + n / 4, 4096);
             cudaError_t e    = cudaMalloc(&p, want);
             if (e != cudaSuccess) { p = nullptr; return e; }
             cap = want;
-            if (zero) return cudaMemset(p, 0, want);
+            if (zero) return cudaMemsetAsync(p, 0, want, s);
             return cudaSuccess;
         }
         void release()
@@ -182,8 +187,6 @@ struct qoipp_b200_ctx {
     bool     enc_trivial = false;  // last encode needed no launch (capacity below the header)
     bool     attrs_set   = false;
     uint32_t ts_ticket = 0;  // encode_ts_kernel: current value of its ticket counter
-    uint32_t dt_ticket = 0;  // decode_ts_kernel: likewise
-    bool     decode_ts = false;      // QOIPP_B200_DECODE_TS=1: thread-serial decode fast path (experimental, see decode_host.inl)
     bool     force_general = false;  // QOIPP_B200_GENERAL=1: always the general kernels (A/B measurements, tests)
     int      dec_coresident = 148;  // CTAs of decode_finish_kernel that fit on the device at once
 
@@ -193,9 +196,7 @@ struct qoipp_b200_ctx {
     {
         const bool grew = carry_bytes > carry.cap;
         if (grew) {
-            cudaError_t e = cudaStreamSynchronize(s);  // an earlier launch may still read the old buffer
-            if (e != cudaSuccess) return e;
-            e = carry.reserve(carry_bytes, true);
+            cudaError_t e = carry.reserve(carry_bytes, s, true);
             if (e != cudaSuccess) return e;
         }
         epoch += span;  // skip the epochs the previous call reserved
@@ -233,9 +234,8 @@ namespace
         if ((e = allow_smem(encode_ts_copy_kernel<3>, kTsCopyWarps * sizeof(TsCopySmem))) != cudaSuccess) return e;
         if ((e = allow_smem(encode_ts_copy_kernel<4>, kTsCopyWarps * sizeof(TsCopySmem))) != cudaSuccess) return e;
         if ((e = dec_set_attrs()) != cudaSuccess) return e;
-        if ((e = allow_smem(decode_ts_kernel, kDtWarps * sizeof(DtWarpSmem))) != cudaSuccess) return e;
         int per_sm = 0;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_finish_kernel, kDecThreads, sizeof(DecSmem))) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_finish_kernel, kWtThreads, kWtSmemBytes)) != cudaSuccess) return e;
         c->dec_coresident = std::max(1, per_sm) * c->sm_count;
         c->attrs_set = true;
         return cudaSuccess;
@@ -272,8 +272,8 @@ namespace
         const uint64_t T     = ts ? (uint64_t)kTsT : (uint64_t)kEncThreads * kEncK;
         const uint64_t tiles = (n_pixels + T - 1) / T;
         if (tiles * n_images >= (1ull << 31)) return H::TooBig;
-        QB_CUDA(c->results.reserve(sizeof(EncResult) * n_images));
-        QB_CUDA(c->tickets.reserve(64, true));
+        QB_CUDA(c->results.reserve(sizeof(EncResult) * n_images, s));
+        QB_CUDA(c->tickets.reserve(64, s, true));
         QB_CUDA(c->next_epoch(tiles * n_images * kEncDescWords * sizeof(uint64_t), s));
         EncParams P{};
         P.in = d_in, P.out = d_out;
@@ -289,10 +289,8 @@ namespace
             const uint64_t n_tiles   = tiles * n_images;
             const uint64_t scr_words = ch == 3 ? TsCfg<3>::kScrWords : TsCfg<4>::kScrWords;
             const uint64_t groups    = (tiles + 63) / 64;
-            if (n_tiles * scr_words * 4 > c->scratch.cap || (n_tiles + groups * n_images) * 4 > c->counts.cap)
-                QB_CUDA(cudaStreamSynchronize(s));  // an earlier launch may still use the buffers
-            QB_CUDA(c->scratch.reserve(n_tiles * scr_words * 4));
-            QB_CUDA(c->counts.reserve((n_tiles + groups * n_images) * 4));
+            QB_CUDA(c->scratch.reserve(n_tiles * scr_words * 4, s));
+            QB_CUDA(c->counts.reserve((n_tiles + groups * n_images) * 4, s));
             P.scratch          = static_cast<uint32_t*>(c->scratch.p);
             P.tile_bytes       = static_cast<uint32_t*>(c->counts.p);
             P.group_bytes      = P.tile_bytes + n_tiles;
@@ -446,7 +444,6 @@ extern "C"
         }
         c->sm_count = prop.multiProcessorCount;
         if (const char* g = std::getenv("QOIPP_B200_GENERAL")) c->force_general = g[0] == '1';
-        if (const char* g = std::getenv("QOIPP_B200_DECODE_TS")) c->decode_ts = g[0] == '1';
         if (const char* g = std::getenv("QOIPP_B200_COPY_THREADS")) c->copy_threads = (unsigned)std::max(0, std::min(16, std::atoi(g)));
         c->copy_threads = std::min(c->copy_threads, std::max(1u, std::thread::hardware_concurrency()) - 1u);
         *out        = c;
@@ -521,13 +518,13 @@ extern "C"
         const uint8_t* d_in  = mapped_host(h_raw);
         uint8_t*       d_out = mapped_host(h_out);
         if (!d_in) {
-            QB_CUDA(c->stage_in.reserve(raw_size + 16));
+            QB_CUDA(c->stage_in.reserve(raw_size + 16, s));
             QB_CUDA(pageable_to_device(c, c->stage_in.p, h_raw, raw_size, s));
             d_in = static_cast<uint8_t*>(c->stage_in.p);
         }
         const bool staged_out = d_out == nullptr;
         if (staged_out) {
-            QB_CUDA(c->stage_out.reserve(cap + 16));
+            QB_CUDA(c->stage_out.reserve(cap + 16, s));
             d_out = static_cast<uint8_t*>(c->stage_out.p);
         }
         const bool in_place = mapped_host(h_raw) != nullptr || !staged_out;  // a kernel touches host memory directly
@@ -573,10 +570,10 @@ extern "C"
         Guard g(c->device);
         // a call can never store more than the worst case of its input (+1 for a pending run flush)
         const uint64_t cap = std::min<uint64_t>(out_cap, n * (ch + 1) + 1);
-        QB_CUDA(c->stage_in.reserve(n * ch + 16));
-        QB_CUDA(c->stage_out.reserve(cap + 16));
-        QB_CUDA(c->state.reserve(sizeof(EncState)));
         cudaStream_t s  = c->own_stream;
+        QB_CUDA(c->stage_in.reserve(n * ch + 16, s));
+        QB_CUDA(c->stage_out.reserve(cap + 16, s));
+        QB_CUDA(c->state.reserve(sizeof(EncState), s));
         auto*        hs = reinterpret_cast<EncState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
         hs->prev = pack_px(st->prev), hs->run = st->run;
         for (int i = 0; i < 64; ++i) hs->table[i] = pack_px(st->seen[i]);

@@ -3,8 +3,7 @@
 // tests/emu/Makefile into tests/emu/libqb_emu.so; never part of libqoipp_b200.so.
 #include "cuda_emu.h"
 
-#include "../../qoipp_b200/csrc/decode_kernel.cuh"
-#include "../../qoipp_b200/csrc/decode_ts.cuh"
+#include "../../qoipp_b200/csrc/decode_wt.cuh"
 #include "../../qoipp_b200/csrc/encode_kernel.cuh"
 #include "../../qoipp_b200/csrc/encode_ts.cuh"
 #include "../../qoipp_b200/csrc/host_util.hpp"
@@ -134,34 +133,18 @@ extern "C"
         DecControl             ctl;
         memset(res.data(), 0, sizeof(DecResult) * n_images);
         memset(&ctl, 0, sizeof ctl);
-        uint32_t ticket = 0;
-        P.desc = desc.data(); P.results = res.data(); P.control = &ctl; P.fix = fix.data(); P.ticket = &ticket;
+        P.desc = desc.data(); P.results = res.data(); P.control = &ctl; P.fix = fix.data();
         P.epoch = 5; P.round = 0;
-        std::vector<uint64_t> fdesc;
-        std::vector<uint32_t> ffirst(n_images + 1);
-        uint32_t              fticket = 0xFFFFFFF8u;
-        if (force_serial == 2) {  // the thread-serial fast path as round 0
-            uint64_t ft = 0;
-            for (uint32_t k = 0; k < n_images; ++k) { ffirst[k] = (uint32_t)ft; ft += (offsets[k + 1] - offsets[k] - host::kHeaderSize + kDtTB - 1) / kDtTB; }
-            ffirst[n_images] = (uint32_t)ft;
-            fdesc.assign((size_t)ft * kDecDescWords, 0);
-            P.fast_used = 1;
-            DtParams F{};
-            F.d = P; F.tile_first = n_images == 1 ? nullptr : ffirst.data(); F.desc = fdesc.data(); F.n_tiles = (uint32_t)ft;
-            F.ticket = &fticket; F.ticket_base = fticket;
-            const unsigned n_ctas = std::min<unsigned>(((unsigned)ft + kDtWarps - 1) / kDtWarps, (unsigned)resident);
-            emu::launch(dim3(n_ctas), dim3(kDtThreads), kDtWarps * sizeof(DtWarpSmem) + 128, [=] { decode_ts_kernel(F); }, resident, seed);
-        } else if (!force_serial) {
-            emu::launch(dim3(P.n_tiles), dim3(kDecThreads), sizeof(DecSmem) + 128, [=] { decode_kernel(P); }, resident, seed);
-            if (ticket != 0) return -1;
+        const unsigned n_ctas = std::max(1u, std::min<unsigned>((P.n_tiles + kWtWarps - 1) / kWtWarps, (unsigned)resident));
+        if (!force_serial) {
+            emu::launch(dim3(n_ctas), dim3(kWtThreads), kWtSmemBytes + 128, [=] { decode_wt_kernel(P); }, (int)n_ctas, seed);
         } else {
             for (auto& r : res) r.first_bad[kDecRounds] = 0xFFFFFFFFu;  // "tile 0 refuted in the last round"
         }
         {   // cooperative launch: every CTA resident
-            const unsigned g = std::min<unsigned>(P.n_tiles, 3u);
-            emu::launch(dim3(g), dim3(kDecThreads), sizeof(DecSmem) + 128, [=] { decode_finish_kernel(P); }, (int)g, seed + 1);
+            emu::launch(dim3(n_ctas), dim3(kWtThreads), kWtSmemBytes + 128, [=] { decode_finish_kernel(P); }, (int)n_ctas, seed + 1);
         }
-        for (uint32_t k = 0; k < n_images; ++k) out_path[k] = (int)res[k].path + (res[k].pad[0] ? 1000 : 0);  // + 1000: fast path refuted
+        for (uint32_t k = 0; k < n_images; ++k) out_path[k] = (int)res[k].path;
         return 0;
     }
 
