@@ -34,6 +34,8 @@
 
 #include "qb_common.cuh"
 
+#include <type_traits>
+
 namespace qb
 {
     struct DecState {  // == StreamDecoder members (include/qoipp/stream.hpp:239-243), pixels packed
@@ -96,6 +98,8 @@ namespace qb
 
     constexpr int kDecDescWords = 72;
     constexpr int kDwParse = 0, kDwPixA = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
+    constexpr int kDwGrp = 68, kDwSup = 69;  // totals of the 64 tiles / 4096 tiles ending with this tile (see wt_gather_pixa)
+    constexpr unsigned kGrp = 64, kSup = 4096;
     constexpr int kFixWords = 16, kFixMax = kFixWords - 1;  // word 0: count | decode tag << 8; entries: pos | alpha << 16
 
     // parse map of a byte range: exit offset for each of the five possible entry offsets.  Entries 0..3 live in the
@@ -125,6 +129,38 @@ namespace qb
         return 1u + ((tag >> 6) == 2u) + 3u * (tag == kOpRgb) + 4u * (tag == kOpRgba);
     }
 
+    // ---- per-tag table shared by the warps of a CTA (2 KB): what the walks need from an op's first byte in one LDS.64
+    //   x: delta of r (bits 0..7) and b (bits 16..23) as two 16-bit lanes: OP_DIFF dr, db; OP_LUMA dg - 8 in both (the second
+    //      byte's nibbles are added by the walk); mod 256 per lane
+    //   y: dg (bits 0..7) | 3dr+5dg+7db mod 64 of that delta (8..13) | op length (14..16) | run - 1 of an OP_RUN (17..22) |
+    //      OP_LUMA (23) | slot-byte flags (24..31): kSlRgb, kSlIdx, both for OP_RUN
+    __device__ __forceinline__ uint2 wt_lut_entry(unsigned tag)
+    {
+        unsigned rb = 0, g = 0, fl = 0, runx = 0, luma = 0;
+        const unsigned hi = tag >> 6;
+        if (tag == kOpRgb) fl = kSlRgb;
+        else if (tag == kOpRgba) fl = 0;
+        else if (hi == 0u) fl = kSlIdx;
+        else if (hi == 1u) {  // simple.cpp:136-144
+            rb = ((((tag >> 4) & 3u) + 254u) & 255u) | ((((tag & 3u) + 254u) & 255u) << 16);
+            g  = (((tag >> 2) & 3u) + 254u) & 255u;
+        } else if (hi == 2u) {  // simple.cpp:145-155
+            g    = (tag + 0x60u) & 255u;  // dg = (tag & 63) - 32
+            rb   = ((g + 248u) & 255u) * 0x00010001u;
+            luma = 1;
+        } else {
+            fl = kSlRgb | kSlIdx, runx = tag & 63u;  // simple.cpp:156-163
+        }
+        const unsigned hc = (3u * (rb & 255u) + 5u * g + 7u * ((rb >> 16) & 255u)) & 63u;
+        return make_uint2(rb, g | hc << 8 | op_length(tag) << 14 | runx << 17 | luma << 23 | fl << 24);
+    }
+    __device__ __forceinline__ void wt_build_lut(uint2* lut)  // all threads of the CTA; ends with a barrier
+    {
+        for (unsigned i = threadIdx.x; i < 256u; i += blockDim.x) lut[i] = wt_lut_entry(i);
+        __syncthreads();
+    }
+    constexpr size_t kWtLutBytes = 256 * sizeof(uint2);
+
     // pixels before a tile (33 bits, saturating) and the alpha of the last OP_RGBA (0x100 | alpha, 0 = none so far)
     struct PixA {
         unsigned lo, hi, a;
@@ -143,8 +179,7 @@ namespace qb
         alignas(16) unsigned char bytes[kDecTB + 48];  // tile bytes at [shift, shift + kDecTB + 8), zero padded
         unsigned       rec[kWtNodes + 3];              // per node: value relative to its base (ops, E nodes, EXT entries)
         unsigned short base[kDecTB + 32];              // per op / E node: base node id
-        unsigned short pix[kDecTB + 4];                // per op: tile-relative pixel offset (+ sentinel)
-        alignas(4) unsigned char slot[kDecTB + 4];     // per op: slot | flags
+        alignas(4) unsigned char slot[kDecTB + 4];     // per op: slot | flags; an OP_RUN keeps its tag byte (0xC0 | run - 1)
         unsigned short lastk[64];                      // last op per slot
         unsigned       fixe[kFixWords];                // learned alphas: pos | alpha << 16
         unsigned       fails[kFixWords];               // OP_RGB ops refuted in this round: op ordinal | actual alpha << 16
@@ -190,6 +225,59 @@ namespace qb
         stream = P.qoi + o0, size = __ldg(P.offsets + lo + 1) - o0;
     }
 
+    // ---- pixels before tile t of its image and the alpha of the last OP_RGBA before it, WITHOUT a chain: every tile
+    // publishes its own count (kDwPixA) right after its parse; the last tile of every 64 (4096) sums its group
+    // (super-group) from those words (kDwGrp / kDwSup, in its own descriptor).  A reader folds <= 63 tile words, <= 63
+    // group words and the super-group words before it: it waits for tiles that started before it to pass their parse,
+    // never for a predecessor's own prefix.  (A chained look-back of this sum moved at 32 tiles per L2 round trip: the
+    // whole decode was bounded by it, profiles/r02_experiments.md.)  All lanes of one warp call this together.
+    template <class Fetch>
+    __device__ __forceinline__ PixA wt_fold32(unsigned n, Fetch fetch)  // elements 0 .. n-1 (n <= 32) in order, lane = element
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        const PixA     v    = lane < n ? fetch(lane) : PixA{ 0u, 0u, 0u };
+        // the sum in three 16/16/1-bit slices (each slice sum fits 32 bits); the alpha of the last element that has one
+        const uint64_t s = (uint64_t)__reduce_add_sync(kFull, v.lo & 0xFFFFu) + ((uint64_t)__reduce_add_sync(kFull, v.lo >> 16) << 16) +
+                           ((uint64_t)__reduce_add_sync(kFull, v.hi) << 32);
+        const unsigned has = __ballot_sync(kFull, (v.a & 0x100u) != 0);
+        const unsigned a   = __shfl_sync(kFull, v.a, has ? 31 - __clz((int)has) : 0);
+        const uint64_t c   = s > kPixSat ? kPixSat : s;
+        return PixA{ (unsigned)c, (unsigned)(c >> 32), has ? a : 0u };
+    }
+    __device__ __forceinline__ PixA wt_wait_pixa(const uint64_t* d_t, unsigned t, unsigned p, int which, const Epochs& ep)
+    {
+        return pixa_unpack(word_payload(wait_word(d_t - (int64_t)(t - p) * kDecDescWords + which, ep, p)));
+    }
+    // sum over tiles [t0, t0 + n) (n <= 64) of word `which`, stride `step` tiles between elements
+    __device__ __forceinline__ PixA wt_fold_words(const uint64_t* d_t, unsigned t, unsigned first, unsigned n, unsigned step, int which, const Epochs& ep)
+    {
+        PixA acc = wt_fold32(min(n, 32u), [&](unsigned i) { return wt_wait_pixa(d_t, t, first + i * step, which, ep); });
+        if (n > 32u) acc = pixa_comb(acc, wt_fold32(n - 32u, [&](unsigned i) { return wt_wait_pixa(d_t, t, first + (32u + i) * step, which, ep); }));
+        return acc;
+    }
+    __device__ __forceinline__ PixA wt_gather_pixa(const uint64_t* d_t, unsigned t, const Epochs& ep)
+    {
+        PixA           acc{ 0u, 0u, 0x1FFu };  // before the stream: no pixels, alpha 255
+        const unsigned s = t / kSup, g = t / kGrp, r = t % kGrp;
+        for (unsigned j = 0; j < s; j += 32u)  // super-groups before mine
+            acc = pixa_comb(acc, wt_fold32(min(32u, s - j), [&](unsigned i) { return wt_wait_pixa(d_t, t, (j + i) * kSup + kSup - 1u, kDwSup, ep); }));
+        const unsigned g0 = s * (kSup / kGrp);  // groups of my super-group before mine
+        if (g > g0) acc = pixa_comb(acc, wt_fold_words(d_t, t, g0 * kGrp + kGrp - 1u, g - g0, kGrp, kDwGrp, ep));
+        if (r) acc = pixa_comb(acc, wt_fold_words(d_t, t, g * kGrp, r, 1u, kDwPixA, ep));  // tiles of my group before me
+        return acc;
+    }
+    // the last tile of a group / super-group publishes the totals (own count `mine` not yet visible through memory)
+    __device__ __forceinline__ void wt_publish_groups(uint64_t* d_t, unsigned t, const PixA& mine, unsigned epoch, const Epochs& ep)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        if (t % kGrp != kGrp - 1u) return;
+        const PixA grp = pixa_comb(wt_fold_words(d_t, t, t - (kGrp - 1u), kGrp - 1u, 1u, kDwPixA, ep), mine);
+        if (lane == 0) st_word(d_t + kDwGrp, pack_word(pixa_pack(grp), ST_INCL, epoch));
+        if (t % kSup != kSup - 1u) return;
+        const PixA sup = pixa_comb(wt_fold_words(d_t, t, t - (kSup - kGrp), kSup / kGrp - 1u, kGrp, kDwGrp, ep), grp);
+        if (lane == 0) st_word(d_t + kDwSup, pack_word(pixa_pack(sup), ST_INCL, epoch));
+    }
+
     // incoming value of state entry `e` (0..63 table slot, 64 prev) of tile `t`: follow the chain of transfer words
     // through the predecessors until a constant (inclusive word) or the start of the stream.  `d_t` = descriptor of tile t.
     __device__ __forceinline__ unsigned wt_resolve_entry(const uint64_t* d_t, unsigned t, unsigned e, const Epochs& ep)
@@ -206,8 +294,8 @@ namespace qb
     }
 
     // one tile (global ticket `gticket`) of round `round`; one warp
-    __device__ __forceinline__ void wt_decode_tile(const DecParams& P, WtSmem& sm, unsigned round, unsigned gticket, unsigned img, unsigned t,
-                                                   unsigned ntiles, const uint8_t* stream, uint64_t size, unsigned fresh_from)
+    __device__ __forceinline__ void wt_decode_tile(const DecParams& P, WtSmem& sm, const uint2* lut, unsigned round, unsigned gticket, unsigned img,
+                                                   unsigned t, unsigned ntiles, const uint8_t* stream, uint64_t size, unsigned fresh_from)
     {
         const unsigned lane = threadIdx.x & 31u;
         [[maybe_unused]] const long long qb_t0 = QB_T0();
@@ -232,6 +320,9 @@ namespace qb
                 if (lane >= 1 && lane <= n) sm.fixe[lane - 1] = fix[lane];
             }
             if (lane == 0) sm.fixn = n, sm.fixn0 = n, sm.fix_dirty = 0, sm.nfail = 0;
+#ifdef QB_EMU_TRACE
+            if (lane == 0 && t == 21) { fprintf(stderr, "LOAD round %u tile %u n %u hdr %08x:", round, t, n, fix[0]); for (unsigned i = 1; i <= n; ++i) fprintf(stderr, " %08x", fix[i]); fprintf(stderr, "\n"); }
+#endif
         }
 
         // ---- stage the tile: 16-byte aligned vectors land at the same misalignment in shared memory
@@ -256,14 +347,17 @@ namespace qb
         // ================= look-back 1: parse map; counts along the path from entry offset 0 =================
         unsigned M0 = 0, R0 = 0, X0 = 0, A0 = kNoPos;  // op starts / OP_RUN ops (bit = byte of the chunk), extra run pixels, last OP_RGBA
         Map      mymap;
+        const unsigned* lut_y = reinterpret_cast<const unsigned*>(lut) + 1;  // word y of entry i at lut_y[2 i]
         {
             unsigned p = cbeg;
             while (p < cend) {
-                const unsigned tag = B[p], bit = 1u << (p - cbeg);
+                const unsigned tag = B[p], y = lut_y[2u * tag], bit = 1u << (p - cbeg);
+                const unsigned rx  = (y >> 17) & 63u;
                 M0 |= bit;
-                if (tag >= 0xC0u && tag < kOpRgb) R0 |= bit, X0 += tag & 63u;
+                X0 += rx;
+                if (rx) R0 |= bit;
                 if (tag == kOpRgba) A0 = p;
-                p += op_length(tag);
+                p += (y >> 14) & 7u;
             }
             const unsigned cfull = cbeg + kWtChunk;
             const unsigned exit0 = p > cfull ? p - cfull : 0u;
@@ -271,7 +365,7 @@ namespace qb
 #pragma unroll 1
             for (unsigned e = 1; e <= 4u; ++e) {  // a late entry usually falls into the path of entry 0 after an op or two
                 unsigned q = cbeg + e;
-                while (q < cend && !((M0 >> (q - cbeg)) & 1u)) q += op_length(B[q]);
+                while (q < cend && !((M0 >> (q - cbeg)) & 1u)) q += (lut_y[2u * B[q]] >> 14) & 7u;
                 win |= (q < cend ? exit0 : (q > cfull ? q - cfull : 0u)) << (3u * e);
             }
             mymap = map_unpack(win);
@@ -287,7 +381,9 @@ namespace qb
         const Map tile_map = Map{ __shfl_sync(kFull, incl_map.lo, 31), __shfl_sync(kFull, incl_map.hi, 31) };
         unsigned  tile_entry;
         {
-            if (lane == 0 && t > 0) st_word(desc + kDwParse, pack_word(map_pack(tile_map), ST_AGG, epoch));
+            // a tile that re-synchronises (nearly all do) exits at the same offset whatever it was entered at: inclusive at once
+            const bool const_map = tile_map.lo == (tile_map.lo & 0xFFu) * 0x01010101u && tile_map.hi == (tile_map.lo & 0xFFu);
+            if (lane == 0 && t > 0) st_word(desc + kDwParse, pack_word(map_pack(tile_map), const_map ? ST_INCL : ST_AGG, epoch));
             const Map in = warp_lookback_lazy<Map>(
                 t, map_const(0), map_identity(),
                 [&](unsigned p, unsigned& st) {
@@ -297,7 +393,7 @@ namespace qb
                 },
                 [](const Map& a, const Map& b) { return map_compose(a, b); });
             tile_entry = in.lo & 7u;  // `in` is constant: every chain ended in an inclusive word
-            if (lane == 0) st_word(desc + kDwParse, pack_word(map_pack(map_const(map_at(tile_map, tile_entry))), ST_INCL, epoch));
+            if (lane == 0 && (t == 0 || !const_map)) st_word(desc + kDwParse, pack_word(map_pack(map_const(map_at(tile_map, tile_entry))), ST_INCL, epoch));
         }
         const unsigned my_entry = map_at(excl_map, tile_entry);
         QB_STAMP(desc, 68, 1, qb_t0);  // parse + look-back 1
@@ -307,11 +403,11 @@ namespace qb
         {
             unsigned p = cbeg + my_entry, own = 0, ownx = 0, Apos = kNoPos, X;
             while (p < cend && !((M0 >> (p - cbeg)) & 1u)) {  // until the path of entry 0 is met
-                const unsigned tag = B[p];
+                const unsigned tag = B[p], y = lut_y[2u * tag];
                 ++own;
-                if (tag >= 0xC0u && tag < kOpRgb) ownx += tag & 63u;
+                ownx += (y >> 17) & 63u;
                 if (tag == kOpRgba) Apos = p;
-                p += op_length(tag);
+                p += (y >> 14) & 7u;
             }
             if (p < cend) {
                 const unsigned rel = p - cbeg;
@@ -332,7 +428,7 @@ namespace qb
                 }
             }
         }
-        unsigned opbase, pixbase, n_ops, n_pix, alpha_lane;
+        unsigned opbase, n_ops, n_pix, alpha_lane;
         uint64_t pix_base;
         {
             const unsigned mine = npx_lane | nops << 16;
@@ -348,73 +444,82 @@ namespace qb
             const unsigned tot = __shfl_sync(kFull, inc, 31), atot = __shfl_sync(kFull, ai, 31);
             unsigned       aex = __shfl_up_sync(kFull, ai, 1);
             if (lane == 0) aex = 0;
-            opbase = (inc - mine) >> 16, pixbase = (inc - mine) & 0xFFFFu;
+            opbase = (inc - mine) >> 16;
             n_ops = tot >> 16, n_pix = tot & 0xFFFFu;
             const PixA agg{ n_pix, 0u, atot };
-            if (lane == 0 && t > 0) st_word(desc + kDwPixA, pack_word(pixa_pack(agg), ST_AGG, epoch));
-            const PixA in = warp_lookback_lazy<PixA>(
-                t, PixA{ 0u, 0u, 0x1FFu }, PixA{ 0u, 0u, 0u },
-                [&](unsigned p, unsigned& st) {
-                    const uint64_t wd = ld_word(word_of(p, kDwPixA));
-                    st                = ep.valid(wd, p) ? raw_status(wd) : (unsigned)ST_NONE;
-                    return pixa_unpack(word_payload(wd));
-                },
-                [](const PixA& a, const PixA& b) { return pixa_comb(a, b); });
-            if (lane == 0) st_word(desc + kDwPixA, pack_word(pixa_pack(pixa_comb(in, agg)), ST_INCL, epoch));
+            if (lane == 0) st_word(desc + kDwPixA, pack_word(pixa_pack(agg), ST_INCL, epoch));
+            wt_publish_groups(desc, t, agg, epoch, ep);
+            const PixA in = wt_gather_pixa(desc, t, ep);
             pix_base   = (uint64_t)in.hi << 32 | in.lo;
             alpha_lane = ((aex & 0x100u) ? aex : in.a) & 255u;
         }
         QB_STAMP(desc, 69, 0, qb_t0);  // counts + look-back 2
 
         // ================= the walk: one record per op =================
-        unsigned       idxm = 0;  // OP_INDEX ops of this lane (bit = op number within the lane)
-        unsigned       exit_bid, exit_h;
-        const unsigned* S32 = reinterpret_cast<const unsigned*>(sm.bytes);
+        // Branch-free for the common ops: the tag's table entry gives the delta (OP_DIFF / OP_LUMA), the slot contribution, the
+        // length and the flags; a literal overrides by selects; only OP_INDEX and learned alphas branch.  r and b accumulate in
+        // two 16-bit lanes of one register (carries stay inside a lane for the <= 28 ops of a chunk), g in another.
+        unsigned idxm = 0;  // OP_INDEX ops of this lane (bit = op number within the lane)
+        unsigned exit_bid, exit_h, exit_rec;
         {
-            unsigned p = cbeg + my_entry, k = opbase, px = pixbase, j = 0;
-            unsigned acc = 0, bid = kIdE + lane, h = 0, alpha = alpha_lane;
+            const unsigned* S32 = reinterpret_cast<const unsigned*>(sm.bytes);
+            unsigned        p = cbeg + my_entry, k = opbase, j = 0;
+            unsigned        arb = 0, ag = 0, atop = 0, bid = kIdE + lane, h = 0, alpha = alpha_lane, recv = 0;
             while (p < cend) {
-                const unsigned a  = shift + p;
-                const unsigned x  = __funnelshift_r(S32[a >> 2], S32[(a >> 2) + 1u], (a & 3u) * 8u);  // the op's first four bytes
+                const unsigned a   = shift + p;
+                const unsigned x   = __funnelshift_r(S32[a >> 2], S32[(a >> 2) + 1u], (a & 3u) * 8u);  // the op's first four bytes
                 const unsigned tag = x & 0xFFu;
-                unsigned       len = 1, npx = 1, fl = 0;
+                const uint2    L   = lut[tag];
+                const unsigned lm  = 0u - ((L.y >> 23) & 1u);                                             // OP_LUMA: all ones
+                const unsigned nib = (((x >> 12) & 15u) | ((x >> 8) & 15u) << 16) & lm;                   // dr - dg + 8, db - dg + 8
+                arb += L.x + nib, ag += L.y;                                                              // bits above 7 of ag are ignored
+                h += (L.y >> 8) + __dp2a_lo(nib, 0x00000703u, 0u);
                 if (tag >= kOpRgb) {  // simple.cpp:119-129; OP_RGB keeps the alpha: speculated here, verified in the emit pass
                     if (tag == kOpRgba) alpha = sm.bytes[a + 4u];
-                    else {
-                        fl = kSlRgb;
-                        if (fixn0)
-                            for (unsigned f = 0; f < fixn0; ++f)
-                                if ((sm.fixe[f] & 0xFFFFu) == p) alpha = (sm.fixe[f] >> 16) & 255u;
-                    }
-                    acc = (x >> 8) | alpha << 24, bid = kIdAbs, h = slot_of(acc), len = 4u + (tag & 1u);
-                } else {
-                    const unsigned hi = tag >> 6;
-                    if (hi == 1u) {  // simple.cpp:136-144
-                        const unsigned d = add4(((tag >> 4) & 3u) | ((tag >> 2) & 3u) << 8 | (tag & 3u) << 16, 0x00FEFEFEu);
-                        acc = add4(acc, d), h += __dp4a(d, 0x00070503u, 0u);
-                    } else if (hi == 2u) {  // simple.cpp:145-155
-                        const unsigned rb = (x >> 8) & 0xFFu, vg = (tag + 0x60u) & 0xFFu;  // dg = (tag & 63) - 32
-                        const unsigned d  = ((vg + (rb >> 4) + 248u) & 255u) | vg << 8 | ((vg + (rb & 15u) + 248u) & 255u) << 16;
-                        acc = add4(acc, d), h += __dp4a(d, 0x00070503u, 0u), len = 2;
-                    } else if (hi == 0u) {  // simple.cpp:132-135: the value is found by the search below
-                        acc = 0, bid = k, h = tag, fl = kSlIdx, idxm |= 1u << j;
-                    } else {
-                        npx = (tag & 63u) + 1u;  // simple.cpp:156-163: repeats the record of the previous op
-                    }
+                    else if (fixn0)
+                        for (unsigned f = 0; f < fixn0; ++f)
+                            if ((sm.fixe[f] & 0xFFFFu) == p) alpha = (sm.fixe[f] >> 16) & 255u;
+                    const unsigned rgb = x >> 8;
+                    arb = rgb & 0x00FF00FFu, ag = rgb >> 8, atop = alpha << 24, bid = kIdAbs;
+                    h = __dp4a(rgb | atop, 0x0B070503u, 0u);
+                } else if (tag < 0x40u) {  // simple.cpp:132-135: the value is found by the search below
+                    arb = 0, ag = 0, atop = 0, bid = k, h = tag, idxm |= 1u << j;
                 }
-                sm.rec[k]  = acc;
+                recv = (__byte_perm(arb, ag, 0x3240) & 0x00FFFFFFu) | atop;
+                const unsigned fl = L.y >> 24;
+                sm.rec[k]  = recv;
                 sm.base[k] = (unsigned short)bid;
-                sm.slot[k] = (unsigned char)((h & 63u) | fl);
-                sm.pix[k]  = (unsigned short)px;
-                px += npx, ++k, ++j, p += len;
+                sm.slot[k] = (unsigned char)(fl == (kSlRgb | kSlIdx) ? tag : ((h & 63u) | fl));  // an OP_RUN keeps its tag
+                ++k, ++j, p += (L.y >> 14) & 7u;
             }
-            exit_bid = bid, exit_h = h & 63u;
+            exit_bid = bid, exit_h = h & 63u, exit_rec = recv;
         }
-        // the lane's entry node: the op before its first one (or the value entering the tile)
-        sm.base[kIdE + lane] = (unsigned short)(opbase ? opbase - 1u : kIdExt + 64u);
-        sm.rec[kIdE + lane]  = 0;
         sm.lastk[lane] = (unsigned short)kNoOp, sm.lastk[lane + 32] = (unsigned short)kNoOp;
-        if (lane == 0) sm.pix[n_ops] = (unsigned short)n_pix;
+        const bool any_idx = __ballot_sync(kFull, idxm != 0) != 0;
+        // `prev` leaving the tile is known already when the last op follows a literal: inclusive at once, the next tile waits less
+        bool prev_done = false;
+        {
+            const unsigned last_lane = 31u - (unsigned)__clz((int)(__ballot_sync(kFull, nops != 0) | 1u));
+            const unsigned lb = __shfl_sync(kFull, exit_bid, (int)last_lane), lr = __shfl_sync(kFull, exit_rec, (int)last_lane);
+            prev_done = n_ops != 0 && lb == kIdAbs;
+            if (prev_done && lane == 0) st_word(desc + kDwState + 64, pack_word(lr, ST_INCL, epoch));
+        }
+        // entry nodes: the value entering lane l's chunk = the value of the op before its first one
+        if (any_idx) {  // general form: an alias of that op, resolved by the pointer jumping below
+            sm.base[kIdE + lane] = (unsigned short)(opbase ? opbase - 1u : kIdExt + 64u);
+            sm.rec[kIdE + lane]  = 0;
+        } else {  // no OP_INDEX in the tile: a lane leaves either an absolute value or (its entry + delta): one warp scan
+            unsigned va = exit_bid == kIdAbs ? 1u : 0u, vv = nops ? exit_rec : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned oa = __shfl_up_sync(kFull, va, d), ov = __shfl_up_sync(kFull, vv, d);
+                if ((int)lane >= d && !va) va = oa, vv = add4(ov, vv);
+            }
+            unsigned ea = __shfl_up_sync(kFull, va, 1), ev = __shfl_up_sync(kFull, vv, 1);
+            if (lane == 0) ea = 0, ev = 0;
+            sm.base[kIdE + lane] = (unsigned short)(ea ? kIdAbs : kIdExt + 64u);
+            sm.rec[kIdE + lane]  = ev;
+        }
         QB_STAMP(desc, 69, 1, qb_t0);  // walk
 
         // ================= look-back 3: slot of the value entering the tile / every lane =================
@@ -457,14 +562,16 @@ namespace qb
             unsigned       s     = 64u + lane;
             if (valid) {
                 const unsigned s8 = sm.slot[k], b = sm.base[k];
-                s = s8 & 63u;
-                if (b >= kIdE && b < kIdExt) {  // before the lane's first root: the walk knew the slot relative to the lane's entry
-                    s          = (s + sm.hE[b - kIdE]) & 63u;
-                    sm.slot[k] = (unsigned char)(s | (s8 & 0xC0u));
+                if (s8 < 0xC0u) {  // an OP_RUN repeats its predecessor: never the only writer of a slot
+                    s = s8 & 63u;
+                    if (b >= kIdE && b < kIdExt) {  // before the lane's first root: the walk knew the slot relative to the lane's entry
+                        s = (s + sm.hE[b - kIdE]) & 63u;
+                        if (any_idx) sm.slot[k] = (unsigned char)(s | (s8 & 0xC0u));  // the searches below compare absolute slots
+                    }
                 }
             }
             const unsigned m = __match_any_sync(kFull, s);
-            if (valid && (m & lanemask_gt(lane)) == 0) sm.lastk[s] = (unsigned short)k;
+            if (s < 64u && (m & lanemask_gt(lane)) == 0) sm.lastk[s] = (unsigned short)k;
             __syncwarp();
         }
         QB_STAMP(desc, 70, 0, qb_t0);  // slots + last writers
@@ -479,8 +586,10 @@ namespace qb
                 unsigned       found = kNoOp;
                 unsigned       keep  = (1u << (8u * (q & 3u))) - 1u;  // first word: only the ops before q
                 for (int wi = (int)(q >> 2); wi >= 0; --wi) {
-                    const unsigned x = (W[wi] & 0x3F3F3F3Fu) ^ pat;            // bytes 0..0x3F, zero where the slot matches
-                    const unsigned m = (0x40404040u - x) & 0x40404040u & keep;  // no borrow crosses a byte
+                    const unsigned wv = W[wi];
+                    const unsigned x  = (wv & 0x3F3F3F3Fu) ^ pat;                // bytes 0..0x3F, zero where the slot matches
+                    const unsigned nr = ~(wv & (wv << 1)) >> 1;                  // bit 6 of a byte: not an OP_RUN (0xC0 | run - 1)
+                    const unsigned m  = (0x40404040u - x) & 0x40404040u & keep & nr;  // no borrow crosses a byte
                     if (m) {
                         found = (unsigned)wi * 4u + ((31u - (unsigned)__clz((int)m)) >> 3);
                         break;
@@ -498,7 +607,7 @@ namespace qb
         __syncwarp();
 
         // ================= pointer jumping over the entry nodes and the OP_INDEX ops =================
-        {
+        if (any_idx) {
             const unsigned maxJ = __reduce_max_sync(kFull, 1u + (unsigned)__popc(idxm));
             for (;;) {
                 bool     changed = false;
@@ -594,39 +703,78 @@ namespace qb
         QB_STAMP(desc, 71, 0, qb_t0);  // state look-back
 
         // ================= emit: values, verification, pixels (lane = op) =================
-        bool     bad   = false;
-        unsigned carry = prev_in;  // value of the op before this step's first one
-        for (unsigned kb = 0; kb < n_ops; kb += 32u) {
-            const unsigned k     = kb + lane;
-            const bool     valid = k < n_ops;
-            unsigned       v = 0, sl = 0, p0 = 0, np = 0;
-            if (valid) {
-                v                = sm.rec[k];
-                const unsigned b = sm.base[k];
-                if (b != kIdAbs) v = add4(v, sm.rec[b]);
-                sl = sm.slot[k], p0 = sm.pix[k], np = sm.pix[k + 1u] - p0;
-            }
-            unsigned up = __shfl_up_sync(kFull, v, 1);
-            if (lane == 0) up = carry;
-            carry = __shfl_sync(kFull, v, 31);
-            const bool live = valid && pix_base + p0 < N;  // ops past the image are never executed by the reference
-            if (live) {
-                if ((sl & kSlRgb) && (v >> 24) != (up >> 24)) {  // simple.cpp:119-123: the alpha is inherited from the previous pixel
-                    bad              = true;
-                    const unsigned f = atomicAdd(&sm.nfail, 1u);
-                    if (f < (unsigned)kFixMax) sm.fails[f] = k | (up >> 24) << 16;
+        bool           bad    = false;
+        const unsigned live_n = pix_base < N ? (unsigned)(N - pix_base < 0xFFFFFFFFull ? N - pix_base : 0xFFFFFFFFull) : 0u;  // pixels of this tile inside the image
+        const unsigned tgt    = P.target;
+        uint8_t* const obase  = out + pix_base * tgt;
+        // FAST: rows top-down and (four-byte pixels) a word-aligned image; else the general store_pixel
+        auto emit = [&](auto fast_tag) {
+            constexpr bool FAST    = decltype(fast_tag)::value;
+            unsigned       carry   = prev_in;  // value of the op before this step's first one
+            unsigned       xcarry  = 0;        // extra OP_RUN pixels before this step
+            const unsigned* recp   = sm.rec + lane;
+            const unsigned short* basep = sm.base + lane;
+            const unsigned char*  slotp = sm.slot + lane;
+            auto put = [&](unsigned po, unsigned val) {  // pixel `po` of this tile
+                if (!FAST) store_pixel(out, pix_base + po, val, P);
+                else if (tgt == 4u) reinterpret_cast<unsigned*>(obase)[po] = val;
+                else {
+                    uint8_t* d = obase + po * 3u;
+                    d[0] = (uint8_t)val, d[1] = (uint8_t)(val >> 8), d[2] = (uint8_t)(val >> 16);
                 }
-                if ((sl & kSlIdx) && slot_of(v) != (sl & 63u)) bad = true;  // a never-written (or mis-predicted) slot was read
-                store_pixel(out, pix_base + p0, v, P);
+            };
+            for (unsigned kb = 0; kb < n_ops; kb += 32u, recp += 32, basep += 32, slotp += 32) {
+                const unsigned k     = kb + lane;
+                const bool     valid = k < n_ops;
+                unsigned       v = 0, sl = 0;
+                if (valid) {
+                    v                = *recp;
+                    const unsigned b = *basep;
+                    sl               = *slotp;
+                    if (b != kIdAbs) v = add4(v, sm.rec[b]);
+                }
+                const unsigned ext = sl >= 0xC0u ? sl & 63u : 0u;  // OP_RUN: run - 1 more pixels
+                // pixel offset of the op = its ordinal + the extra run pixels before it (a scan only in steps that hold an OP_RUN)
+                unsigned       p0    = k + xcarry;
+                const unsigned runs0 = __ballot_sync(kFull, ext != 0);
+                if (runs0) {
+                    unsigned inc = ext;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned o = __shfl_up_sync(kFull, inc, d);
+                        if ((int)lane >= d) inc += o;
+                    }
+                    p0 += inc - ext;
+                    xcarry += __shfl_sync(kFull, inc, 31);
+                }
+                unsigned up = __shfl_up_sync(kFull, v, 1);
+                if (lane == 0) up = carry;
+                carry = __shfl_sync(kFull, v, 31);
+                const bool live = valid && p0 < live_n;  // ops past the image are never executed by the reference
+                if (live) {
+                    // flags: kSlRgb alone = OP_RGB (simple.cpp:119-123: the alpha is inherited from the previous pixel), kSlIdx alone =
+                    // OP_INDEX (a never-written or mis-predicted slot was read when the value does not hash to it)
+                    if ((sl & 0xC0u) == kSlRgb && ((v ^ up) >> 24) != 0) {
+                        bad              = true;
+                        const unsigned f = atomicAdd(&sm.nfail, 1u);
+                        if (f < (unsigned)kFixMax) sm.fails[f] = k | (up >> 24) << 16;
+                    }
+                    if ((sl & 0xC0u) == kSlIdx && slot_of(v) != (sl & 63u)) bad = true;
+                    put(p0, v);
+                }
+                if (runs0) {  // OP_RUN pixels are written by the whole warp (clamped, simple.cpp:158)
+                    unsigned runs = runs0 & __ballot_sync(kFull, live);
+                    while (runs) {
+                        const int src = __ffs((int)runs) - 1;
+                        runs &= runs - 1u;
+                        const unsigned rp = __shfl_sync(kFull, p0, src), rn = __shfl_sync(kFull, ext, src), rv = __shfl_sync(kFull, v, src);
+                        for (unsigned j = 1u + lane; j <= rn && rp + j < live_n; j += 32u) put(rp + j, rv);
+                    }
+                }
             }
-            unsigned runs = __ballot_sync(kFull, live && np > 1u);  // OP_RUN pixels are written by the whole warp (clamped, simple.cpp:158)
-            while (runs) {
-                const int src = __ffs((int)runs) - 1;
-                runs &= runs - 1u;
-                const unsigned rp = __shfl_sync(kFull, p0, src), rn = __shfl_sync(kFull, np, src), rv = __shfl_sync(kFull, v, src);
-                for (unsigned j = 1u + lane; j < rn && pix_base + rp + j < N; j += 32u) store_pixel(out, pix_base + rp + j, rv, P);
-            }
-        }
+        };
+        if (!P.flip && (tgt == 3u || (reinterpret_cast<uintptr_t>(out) & 3u) == 0)) emit(std::true_type{});
+        else emit(std::false_type{});
         // a refuted tile makes the image eligible for the next round, from the first such tile on
         if (__ballot_sync(kFull, bad)) {
             if (lane == 0) {
@@ -645,6 +793,9 @@ namespace qb
                     unsigned j = 0;
                     for (; j < sm.fixn; ++j)
                         if ((sm.fixe[j] & 0xFFFFu) == p) break;
+#ifdef QB_EMU_TRACE
+                    if (t == 21) fprintf(stderr, "MERGE round %u f %u k %u actual %02x p %03x j %u fixn %u\n", round, f, k, actual, p, j, sm.fixn);
+#endif
                     if (j < (unsigned)kFixMax) {
                         sm.fixe[j] = p | actual << 16;
                         if (j == sm.fixn) sm.fixn = j + 1u;
@@ -686,8 +837,10 @@ namespace qb
     // waits for is held by a warp that is running too or done
     __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_wt_kernel(const DecParams P)
     {
-        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM)[threadIdx.x >> 5];
+        uint2*         lut  = reinterpret_cast<uint2*>(QB_DYN_SMEM);
+        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM + kWtLutBytes)[threadIdx.x >> 5];
         const unsigned lane = threadIdx.x & 31u;
+        wt_build_lut(lut);
         for (;;) {
             unsigned x = 0;
             if (lane == 0) x = atomicAdd(&P.control->tickets[0], 1u);
@@ -697,7 +850,7 @@ namespace qb
             const uint8_t* stream;
             uint64_t       size;
             locate_image(P, x, img, t, ntiles, stream, size);
-            wt_decode_tile(P, sm, 0u, x, img, t, ntiles, stream, size, 0u);
+            wt_decode_tile(P, sm, lut, 0u, x, img, t, ntiles, stream, size, 0u);
         }
     }
 
@@ -762,7 +915,10 @@ namespace qb
             const uint64_t* d   = d_r - kDecDescWords;
             const Epochs    ep{ P.epoch + (unsigned)kDecRounds + 1u, P.epoch, restart };  // any epoch of this decode is final below `restart`
             pos                 = (uint64_t)restart * kDecTB + (word_payload(d[kDwParse]) & 7u);
-            px                  = word_payload(d[kDwPixA]) & kPixSat;
+            {
+                const PixA before = wt_gather_pixa(d_r, restart, ep);
+                px                = (uint64_t)before.hi << 32 | before.lo;
+            }
             prev                = wt_resolve_entry(d_r, restart, 64u, ep);
             sm.table[lane] = wt_resolve_entry(d_r, restart, lane, ep), sm.table[lane + 32] = wt_resolve_entry(d_r, restart, lane + 32u, ep);
             prev = __shfl_sync(kFull, prev, 0);
@@ -846,7 +1002,8 @@ namespace qb
         decode_serial_body(S, *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM), 0u);
     }
 
-    constexpr size_t kWtSmemBytes = sizeof(WtSmem) * kWtWarps > sizeof(SerialSmem) ? sizeof(WtSmem) * kWtWarps : sizeof(SerialSmem);
+    constexpr size_t kWtSmemBytes = kWtLutBytes + (sizeof(WtSmem) * kWtWarps > sizeof(SerialSmem) ? sizeof(WtSmem) * kWtWarps : sizeof(SerialSmem));
+    static_assert(sizeof(WtSmem) % 16 == 0, "per-warp areas stay 16-byte aligned");
 
     // Everything after round 0, in ONE cooperative launch of co-resident persistent CTAs (so that an image that
     // verified costs a single empty launch): rounds 1..kDecRounds re-decode, per image, the tiles from the first refuted
@@ -854,8 +1011,11 @@ namespace qb
     // last round is decoded by the sequential loop, one warp per image, resuming behind the last verified tile.
     __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_finish_kernel(const DecParams P)
     {
-        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM)[threadIdx.x >> 5];
+        uint2*         lut  = reinterpret_cast<uint2*>(QB_DYN_SMEM);
+        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM + kWtLutBytes)[threadIdx.x >> 5];
         const unsigned lane = threadIdx.x & 31u;
+        if (P.control->any_bad[0] == 0 && P.control->any_bad[kDecRounds] == 0) return;  // everything verified in round 0 (same value in every CTA)
+        wt_build_lut(lut);
         for (unsigned round = 1; round <= (unsigned)kDecRounds; ++round) {
             if (P.control->any_bad[round - 1] == 0) break;  // same value in every CTA: final since the last barrier
             for (;;) {
@@ -869,7 +1029,7 @@ namespace qb
                 locate_image(P, x, img, t, ntiles, stream, size);
                 const unsigned fb = P.results[img].first_bad[round - 1];
                 if (fb == 0 || t < 0xFFFFFFFFu - fb) continue;  // image verified, or a tile before the first refuted one: final
-                wt_decode_tile(P, sm, round, x, img, t, ntiles, stream, size, 0xFFFFFFFFu - fb);
+                wt_decode_tile(P, sm, lut, round, x, img, t, ntiles, stream, size, 0xFFFFFFFFu - fb);
             }
             QB_GRID_SYNC();
         }

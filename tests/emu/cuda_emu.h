@@ -345,6 +345,7 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { u
 static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned s) { uint64_t v = ((uint64_t)hi << 32) | lo; return (unsigned)(v >> (s > 32 ? 32 : s)); }
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) { uint64_t v = ((uint64_t)hi << 32) | lo; return (unsigned)((v << (s & 31)) >> 32); }
 static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) { for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u); return c; }
+static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) { return c + (a & 0xFFFFu) * (b & 255u) + (a >> 16) * ((b >> 8) & 255u); }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
 {
     uint64_t v = ((uint64_t)y << 32) | x; unsigned r = 0;

@@ -140,10 +140,15 @@ extern "C"
             emu::launch(dim3(n_ctas), dim3(kWtThreads), kWtSmemBytes + 128, [=] { decode_wt_kernel(P); }, (int)n_ctas, seed);
         } else {
             for (auto& r : res) r.first_bad[kDecRounds] = 0xFFFFFFFFu;  // "tile 0 refuted in the last round"
+            ctl.any_bad[kDecRounds] = 1;
         }
         {   // cooperative launch: every CTA resident
             emu::launch(dim3(n_ctas), dim3(kWtThreads), kWtSmemBytes + 128, [=] { decode_finish_kernel(P); }, (int)n_ctas, seed + 1);
         }
+        if (getenv("QB_EMU_DEBUG"))
+            for (uint32_t k = 0; k < n_images; ++k)
+                fprintf(stderr, "img %u: bad %u path %u first_bad %x %x %x %x %x pixels %llu\n", k, res[k].bad, res[k].path, res[k].first_bad[0],
+                        res[k].first_bad[1], res[k].first_bad[2], res[k].first_bad[3], res[k].first_bad[4], (unsigned long long)res[k].pixels);
         for (uint32_t k = 0; k < n_images; ++k) out_path[k] = (int)res[k].path;
         return 0;
     }
