@@ -36,6 +36,11 @@
 
 #include <type_traits>
 
+// The decode kernel is bounded by instruction fetch when its hot path does not fit the SM's 32 KB instruction cache
+// (profiles/r02_experiments.md: 98 KB of SASS, hit rate 88 %, time proportional to the number of tiles whatever the
+// occupancy).  Helpers that are called once per tile, or are cold, are real calls instead of inlined copies.
+#define QB_NOINLINE __noinline__
+
 namespace qb
 {
     struct DecState {  // == StreamDecoder members (include/qoipp/stream.hpp:239-243), pixels packed
@@ -93,10 +98,17 @@ namespace qb
 
     // node ids: op ordinals 0 .. kDecTB - 1, lane entry nodes, entries of the state entering the tile, "absolute"
     constexpr unsigned kIdE = kDecTB, kIdExt = kDecTB + 32, kIdAbs = 0xFFFFu, kNoOp = 0xFFFFu, kNoPos = 0xFFFFu;
-    constexpr int      kWtNodes = kDecTB + 32 + 65;
+    // "absolute r, g, b; alpha = the alpha entering the tile" (an OP_RGB before the tile's first alpha setter): a node whose
+    // value is alpha << 24, so that a record based on it needs no special case; filled in when the alpha is gathered (late)
+    constexpr unsigned kIdAbsA = kIdExt + 66u;
+    constexpr int      kWtNodes = kDecTB + 32 + 67;
     constexpr unsigned kSlRgb = 0x40u, kSlIdx = 0x80u;  // flags beside the 6-bit slot
 
+#ifdef QB_TIMING
+    constexpr int kDecDescWords = 80;  // development build: words 72..79 hold phase stamps (tools/phase_probe_wt.py)
+#else
     constexpr int kDecDescWords = 72;
+#endif
     constexpr int kDwParse = 0, kDwPixA = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
     constexpr int kDwGrp = 68, kDwSup = 69;  // totals of the 64 tiles / 4096 tiles ending with this tile (see wt_gather_pixa)
     constexpr unsigned kGrp = 64, kSup = 4096;
@@ -188,7 +200,7 @@ namespace qb
     };
 
     // store one pixel (target 3 or 4 bytes), optionally bottom-up rows (simple.cpp:401-408 done in place)
-    __device__ __forceinline__ void store_pixel(uint8_t* out, uint64_t pix, unsigned val, const DecParams& P)
+    __device__ QB_NOINLINE void store_pixel(uint8_t* out, uint64_t pix, unsigned val, const DecParams& P)
     {
         if (P.flip) {
             const uint64_t y = pix / P.width, x = pix - y * P.width;
@@ -249,25 +261,30 @@ namespace qb
         return pixa_unpack(word_payload(wait_word(d_t - (int64_t)(t - p) * kDecDescWords + which, ep, p)));
     }
     // sum over tiles [t0, t0 + n) (n <= 64) of word `which`, stride `step` tiles between elements
-    __device__ __forceinline__ PixA wt_fold_words(const uint64_t* d_t, unsigned t, unsigned first, unsigned n, unsigned step, int which, const Epochs& ep)
+    __device__ QB_NOINLINE PixA wt_fold_words(const uint64_t* d_t, unsigned t, unsigned first, unsigned n, unsigned step, int which, const Epochs& ep)
     {
-        PixA acc = wt_fold32(min(n, 32u), [&](unsigned i) { return wt_wait_pixa(d_t, t, first + i * step, which, ep); });
-        if (n > 32u) acc = pixa_comb(acc, wt_fold32(n - 32u, [&](unsigned i) { return wt_wait_pixa(d_t, t, first + (32u + i) * step, which, ep); }));
+        PixA acc{ 0u, 0u, 0u };
+#pragma unroll 1
+        for (unsigned o = 0; o < n; o += 32u)
+            acc = pixa_comb(acc, wt_fold32(min(n - o, 32u), [&](unsigned i) { return wt_wait_pixa(d_t, t, first + (o + i) * step, which, ep); }));
         return acc;
     }
-    __device__ __forceinline__ PixA wt_gather_pixa(const uint64_t* d_t, unsigned t, const Epochs& ep)
+    __device__ QB_NOINLINE PixA wt_gather_pixa(const uint64_t* d_t, unsigned t, const Epochs& ep)
     {
+        // (A variant that issued the tile-word and group-word loads of a lane together, four in flight, decoded wrongly on
+        // the B200 although it is equivalent on paper and passes in the emulator -- profiles/r02_experiments.md; the folds
+        // stay one after the other.)
         PixA           acc{ 0u, 0u, 0x1FFu };  // before the stream: no pixels, alpha 255
         const unsigned s = t / kSup, g = t / kGrp, r = t % kGrp;
-        for (unsigned j = 0; j < s; j += 32u)  // super-groups before mine
-            acc = pixa_comb(acc, wt_fold32(min(32u, s - j), [&](unsigned i) { return wt_wait_pixa(d_t, t, (j + i) * kSup + kSup - 1u, kDwSup, ep); }));
+        for (unsigned j = 0; j < s; j += 64u)  // super-groups before mine
+            acc = pixa_comb(acc, wt_fold_words(d_t, t, j * kSup + kSup - 1u, min(64u, s - j), kSup, kDwSup, ep));
         const unsigned g0 = s * (kSup / kGrp);  // groups of my super-group before mine
         if (g > g0) acc = pixa_comb(acc, wt_fold_words(d_t, t, g0 * kGrp + kGrp - 1u, g - g0, kGrp, kDwGrp, ep));
         if (r) acc = pixa_comb(acc, wt_fold_words(d_t, t, g * kGrp, r, 1u, kDwPixA, ep));  // tiles of my group before me
         return acc;
     }
     // the last tile of a group / super-group publishes the totals (own count `mine` not yet visible through memory)
-    __device__ __forceinline__ void wt_publish_groups(uint64_t* d_t, unsigned t, const PixA& mine, unsigned epoch, const Epochs& ep)
+    __device__ QB_NOINLINE void wt_publish_groups(uint64_t* d_t, unsigned t, const PixA& mine, unsigned epoch, const Epochs& ep)
     {
         const unsigned lane = threadIdx.x & 31u;
         if (t % kGrp != kGrp - 1u) return;
@@ -280,7 +297,7 @@ namespace qb
 
     // incoming value of state entry `e` (0..63 table slot, 64 prev) of tile `t`: follow the chain of transfer words
     // through the predecessors until a constant (inclusive word) or the start of the stream.  `d_t` = descriptor of tile t.
-    __device__ __forceinline__ unsigned wt_resolve_entry(const uint64_t* d_t, unsigned t, unsigned e, const Epochs& ep)
+    __device__ QB_NOINLINE unsigned wt_resolve_entry(const uint64_t* d_t, unsigned t, unsigned e, const Epochs& ep)
     {
         unsigned acc = 0;
         for (int p = (int)t - 1;; --p) {
@@ -290,6 +307,122 @@ namespace qb
             if (raw_status(wd) == ST_INCL) return add4((unsigned)pl, acc);
             acc = add4(acc, (unsigned)pl);
             e   = (unsigned)(pl >> 32);
+        }
+    }
+
+    // alpha learned by an earlier round for the OP_RGB at byte `p` of the tile, if any (cold: retry rounds only)
+    __device__ QB_NOINLINE bool wt_fix_lookup(const WtSmem& sm, unsigned p, unsigned& alpha)
+    {
+        bool hit = false;
+#pragma unroll 1
+        for (unsigned f = 0; f < sm.fixn0; ++f)
+            if ((sm.fixe[f] & 0xFFFFu) == p) alpha = (sm.fixe[f] >> 16) & 255u, hit = true;
+        return hit;
+    }
+
+    // OP_INDEX ops of a tile (tiles without one never come here): every OP_INDEX finds the last earlier op with its slot
+    // (backward search over the packed slot bytes), then pointer jumping over the lanes' entry nodes and the OP_INDEX ops
+    // ends every node in ABS or in an entry of the state entering the tile.  One warp.
+    __device__ QB_NOINLINE void wt_resolve_index(WtSmem& sm, unsigned idxm, unsigned opbase, unsigned& need_lo, unsigned& need_hi)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        {
+            const unsigned* W = reinterpret_cast<const unsigned*>(sm.slot);
+            for (unsigned bits = idxm; bits; bits &= bits - 1u) {
+                const unsigned q = opbase + (unsigned)__ffs((int)bits) - 1u, s = sm.slot[q] & 63u;
+                const unsigned pat = s * 0x01010101u;
+                unsigned       found = kNoOp;
+                unsigned       keep  = (1u << (8u * (q & 3u))) - 1u;  // first word: only the ops before q
+                for (int wi = (int)(q >> 2); wi >= 0; --wi) {
+                    const unsigned wv = W[wi];
+                    const unsigned x  = (wv & 0x3F3F3F3Fu) ^ pat;                // bytes 0..0x3F, zero where the slot matches
+                    const unsigned nr = ~(wv & (wv << 1)) >> 1;                  // bit 6 of a byte: not an OP_RUN (0xC0 | run - 1)
+                    const unsigned m  = (0x40404040u - x) & 0x40404040u & keep & nr;  // no borrow crosses a byte
+                    if (m) {
+                        found = (unsigned)wi * 4u + ((31u - (unsigned)__clz((int)m)) >> 3);
+                        break;
+                    }
+                    keep = 0xFFFFFFFFu;
+                }
+                if (found != kNoOp) sm.base[q] = (unsigned short)found;
+                else {
+                    sm.base[q] = (unsigned short)(kIdExt + s);
+                    if (s < 32u) need_lo |= 1u << s;
+                    else need_hi |= 1u << (s - 32u);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ================= pointer jumping over the entry nodes and the OP_INDEX ops =================
+        {
+            const unsigned maxJ = __reduce_max_sync(kFull, 1u + (unsigned)__popc(idxm));
+            for (;;) {
+                bool     changed = false;
+                unsigned bits    = idxm;
+                for (unsigned i = 0; i < maxJ; ++i) {
+                    unsigned x = kNoOp;
+                    if (i == 0) x = kIdE + lane;
+                    else if (bits) x = opbase + (unsigned)__ffs((int)bits) - 1u, bits &= bits - 1u;
+                    unsigned nb = 0, nr = 0;
+                    bool     upd = false;
+                    if (x != kNoOp) {
+                        const unsigned b = sm.base[x];
+                        if (b < kIdExt) nb = sm.base[b], nr = add4(sm.rec[x], sm.rec[b]), upd = true;
+                    }
+                    __syncwarp();  // every lane has read its target before any node changes
+                    if (upd) sm.base[x] = (unsigned short)nb, sm.rec[x] = nr, changed = true;
+                    __syncwarp();
+                }
+                if (!__ballot_sync(kFull, changed)) break;
+            }
+            // entries of the incoming state the nodes end in
+            unsigned bits = idxm;
+            for (unsigned i = 0; i <= (unsigned)__popc(idxm); ++i) {
+                unsigned x = kIdE + lane;
+                if (i) x = opbase + (unsigned)__ffs((int)bits) - 1u, bits &= bits - 1u;
+                const unsigned b = sm.base[x];
+                if (b >= kIdExt && b < kIdExt + 64u) {
+                    const unsigned e = b - kIdExt;
+                    if (e < 32u) need_lo |= 1u << e;
+                    else need_hi |= 1u << (e - 32u);
+                }
+            }
+        }
+    }
+
+    // A tile whose verification failed: flag the image for the next round and remember, for every refuted OP_RGB, the alpha
+    // it actually saw (exact if everything before it was exact).  Cold.  One warp.
+    __device__ QB_NOINLINE void wt_record_failures(const DecParams& P, WtSmem& sm, unsigned round, DecResult* res, unsigned t, uint32_t* fix,
+                                                   const unsigned char* B, unsigned first_pos, unsigned opbase, unsigned nops)
+    {
+        const unsigned lane = threadIdx.x & 31u;
+        if (lane == 0) {
+            if (round == 0) atomicOr(&res->bad, 1u);
+            atomicMax(&res->first_bad[round], 0xFFFFFFFFu - t);
+            P.control->any_bad[round] = 1;
+        }
+        __syncwarp();
+        const unsigned nf = min(sm.nfail, (unsigned)kFixMax);
+        for (unsigned f = 0; f < nf; ++f) {
+            const unsigned k = sm.fails[f] & 0xFFFFu, actual = sm.fails[f] >> 16;
+            if (k >= opbase && k < opbase + nops) {  // the owning lane walks to the op's byte position
+                unsigned p = first_pos;
+                for (unsigned i = opbase; i < k; ++i) p += op_length(B[p]);
+                unsigned j = 0;
+                for (; j < sm.fixn; ++j)
+                    if ((sm.fixe[j] & 0xFFFFu) == p) break;
+                if (j < (unsigned)kFixMax) {
+                    sm.fixe[j] = p | actual << 16;
+                    if (j == sm.fixn) sm.fixn = j + 1u;
+                    sm.fix_dirty = 1;
+                }
+            }
+            __syncwarp();
+        }
+        if (sm.fix_dirty && lane < (unsigned)kFixWords) {
+            const unsigned n = min(sm.fixn, (unsigned)kFixMax);
+            fix[lane] = lane == 0 ? (n | (P.epoch & 0xFFFFFFu) << 8) : (lane <= n ? sm.fixe[lane - 1] : 0u);
         }
     }
 
@@ -320,9 +453,6 @@ namespace qb
                 if (lane >= 1 && lane <= n) sm.fixe[lane - 1] = fix[lane];
             }
             if (lane == 0) sm.fixn = n, sm.fixn0 = n, sm.fix_dirty = 0, sm.nfail = 0;
-#ifdef QB_EMU_TRACE
-            if (lane == 0 && t == 21) { fprintf(stderr, "LOAD round %u tile %u n %u hdr %08x:", round, t, n, fix[0]); for (unsigned i = 1; i <= n; ++i) fprintf(stderr, " %08x", fix[i]); fprintf(stderr, "\n"); }
-#endif
         }
 
         // ---- stage the tile: 16-byte aligned vectors land at the same misalignment in shared memory
@@ -342,7 +472,7 @@ namespace qb
         const unsigned       fixn0 = sm.fixn0;
         const unsigned       cbeg  = lane * kWtChunk;
         const unsigned       cend  = min(cbeg + (unsigned)kWtChunk, limit);  // ops of this lane start below cend
-        QB_STAMP(desc, 68, 0, qb_t0);  // ticket + staging
+        QB_STAMP(desc, 72, 0, qb_t0);  // ticket + staging
 
         // ================= look-back 1: parse map; counts along the path from entry offset 0 =================
         unsigned M0 = 0, R0 = 0, X0 = 0, A0 = kNoPos;  // op starts / OP_RUN ops (bit = byte of the chunk), extra run pixels, last OP_RGBA
@@ -396,7 +526,7 @@ namespace qb
             if (lane == 0 && (t == 0 || !const_map)) st_word(desc + kDwParse, pack_word(map_pack(map_const(map_at(tile_map, tile_entry))), ST_INCL, epoch));
         }
         const unsigned my_entry = map_at(excl_map, tile_entry);
-        QB_STAMP(desc, 68, 1, qb_t0);  // parse + look-back 1
+        QB_STAMP(desc, 72, 1, qb_t0);  // parse + look-back 1
 
         // ================= counts of the true path, look-back 2: pixels and inherited alpha =================
         unsigned nops, npx_lane, a_sum;  // a_sum: 0x100 | alpha after this lane's last alpha setter, 0 = none
@@ -422,14 +552,14 @@ namespace qb
             npx_lane = nops + X;
             a_sum    = Apos != kNoPos ? 0x100u | B[Apos + 4u] : 0u;
             if (fixn0) {  // a learned alpha acts like an OP_RGBA from its op on
+#pragma unroll 1
                 for (unsigned j = 0; j < fixn0; ++j) {
                     const unsigned fp = sm.fixe[j] & 0xFFFFu;
                     if (fp >= cbeg + my_entry && fp < cend && (Apos == kNoPos || fp > Apos)) Apos = fp, a_sum = 0x100u | ((sm.fixe[j] >> 16) & 255u);
                 }
             }
         }
-        unsigned opbase, n_ops, n_pix, alpha_lane;
-        uint64_t pix_base;
+        unsigned opbase, n_ops, n_pix, alpha_lane;  // alpha_lane: 0x100 | alpha when an earlier lane of this tile sets it, else 0
         {
             const unsigned mine = npx_lane | nops << 16;
             unsigned       inc  = mine, ai = a_sum;
@@ -448,12 +578,10 @@ namespace qb
             n_ops = tot >> 16, n_pix = tot & 0xFFFFu;
             const PixA agg{ n_pix, 0u, atot };
             if (lane == 0) st_word(desc + kDwPixA, pack_word(pixa_pack(agg), ST_INCL, epoch));
-            wt_publish_groups(desc, t, agg, epoch, ep);
-            const PixA in = wt_gather_pixa(desc, t, ep);
-            pix_base   = (uint64_t)in.hi << 32 | in.lo;
-            alpha_lane = ((aex & 0x100u) ? aex : in.a) & 255u;
+            if (t % kGrp == kGrp - 1u) wt_publish_groups(desc, t, agg, epoch, ep);
+            alpha_lane = aex;
         }
-        QB_STAMP(desc, 69, 0, qb_t0);  // counts + look-back 2
+        QB_STAMP(desc, 73, 0, qb_t0);  // counts
 
         // ================= the walk: one record per op =================
         // Branch-free for the common ops: the tag's table entry gives the delta (OP_DIFF / OP_LUMA), the slot contribution, the
@@ -464,7 +592,8 @@ namespace qb
         {
             const unsigned* S32 = reinterpret_cast<const unsigned*>(sm.bytes);
             unsigned        p = cbeg + my_entry, k = opbase, j = 0;
-            unsigned        arb = 0, ag = 0, atop = 0, bid = kIdE + lane, h = 0, alpha = alpha_lane, recv = 0;
+            unsigned        arb = 0, ag = 0, atop = 0, bid = kIdE + lane, h = 0, alpha = alpha_lane & 255u, recv = 0;
+            unsigned        lit_bid = (alpha_lane & 0x100u) ? kIdAbs : kIdAbsA;  // base of a literal: its alpha is known / the tile's entry alpha
             while (p < cend) {
                 const unsigned a   = shift + p;
                 const unsigned x   = __funnelshift_r(S32[a >> 2], S32[(a >> 2) + 1u], (a & 3u) * 8u);  // the op's first four bytes
@@ -475,12 +604,10 @@ namespace qb
                 arb += L.x + nib, ag += L.y;                                                              // bits above 7 of ag are ignored
                 h += (L.y >> 8) + __dp2a_lo(nib, 0x00000703u, 0u);
                 if (tag >= kOpRgb) {  // simple.cpp:119-129; OP_RGB keeps the alpha: speculated here, verified in the emit pass
-                    if (tag == kOpRgba) alpha = sm.bytes[a + 4u];
-                    else if (fixn0)
-                        for (unsigned f = 0; f < fixn0; ++f)
-                            if ((sm.fixe[f] & 0xFFFFu) == p) alpha = (sm.fixe[f] >> 16) & 255u;
+                    if (tag == kOpRgba) alpha = sm.bytes[a + 4u], lit_bid = kIdAbs;
+                    else if (fixn0 && wt_fix_lookup(sm, p, alpha)) lit_bid = kIdAbs;
                     const unsigned rgb = x >> 8;
-                    arb = rgb & 0x00FF00FFu, ag = rgb >> 8, atop = alpha << 24, bid = kIdAbs;
+                    arb = rgb & 0x00FF00FFu, ag = rgb >> 8, atop = alpha << 24, bid = lit_bid;  // alpha = 0 while it is provisional
                     h = __dp4a(rgb | atop, 0x0B070503u, 0u);
                 } else if (tag < 0x40u) {  // simple.cpp:132-135: the value is found by the search below
                     arb = 0, ag = 0, atop = 0, bid = k, h = tag, idxm |= 1u << j;
@@ -494,8 +621,18 @@ namespace qb
             }
             exit_bid = bid, exit_h = h & 63u, exit_rec = recv;
         }
-        sm.lastk[lane] = (unsigned short)kNoOp, sm.lastk[lane + 32] = (unsigned short)kNoOp;
+        QB_STAMP(desc, 77, 1, qb_t0);  // walk loop
+        sm.lastk[lane] = 0, sm.lastk[lane + 32] = 0;
         const bool any_idx = __ballot_sync(kFull, idxm != 0) != 0;
+        // ---- look-back 2 (no chain, see wt_gather_pixa): pixels before the tile and the alpha entering it.  Taken AFTER the
+        // walk: by now the tiles before this one have long published their counts (before the walk, every tile waited here for
+        // the slowest of all its predecessors to finish parsing: a third of the tile time).
+        const PixA     pin      = wt_gather_pixa(desc, t, ep);
+        const uint64_t pix_base = (uint64_t)pin.hi << 32 | pin.lo;
+        const unsigned ain      = pin.a & 255u;
+        if (lane == 0) sm.rec[kIdAbsA] = ain << 24;
+        QB_STAMP(desc, 76, 0, qb_t0);  // walk + gather
+        if (exit_bid == kIdAbsA) exit_h = (exit_h + 11u * ain) & 63u;  // util.hpp:347-351: the alpha's share of the slot
         // `prev` leaving the tile is known already when the last op follows a literal: inclusive at once, the next tile waits less
         bool prev_done = false;
         {
@@ -509,7 +646,7 @@ namespace qb
             sm.base[kIdE + lane] = (unsigned short)(opbase ? opbase - 1u : kIdExt + 64u);
             sm.rec[kIdE + lane]  = 0;
         } else {  // no OP_INDEX in the tile: a lane leaves either an absolute value or (its entry + delta): one warp scan
-            unsigned va = exit_bid == kIdAbs ? 1u : 0u, vv = nops ? exit_rec : 0u;
+            unsigned va = exit_bid == kIdAbs ? 1u : (exit_bid == kIdAbsA ? 2u : 0u), vv = nops ? exit_rec : 0u;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const unsigned oa = __shfl_up_sync(kFull, va, d), ov = __shfl_up_sync(kFull, vv, d);
@@ -517,10 +654,10 @@ namespace qb
             }
             unsigned ea = __shfl_up_sync(kFull, va, 1), ev = __shfl_up_sync(kFull, vv, 1);
             if (lane == 0) ea = 0, ev = 0;
-            sm.base[kIdE + lane] = (unsigned short)(ea ? kIdAbs : kIdExt + 64u);
+            sm.base[kIdE + lane] = (unsigned short)(ea == 1u ? kIdAbs : (ea == 2u ? kIdAbsA : kIdExt + 64u));
             sm.rec[kIdE + lane]  = ev;
         }
-        QB_STAMP(desc, 69, 1, qb_t0);  // walk
+        QB_STAMP(desc, 73, 1, qb_t0);  // walk
 
         // ================= look-back 3: slot of the value entering the tile / every lane =================
         {
@@ -555,93 +692,46 @@ namespace qb
         }
         __syncwarp();
 
+        QB_STAMP(desc, 76, 1, qb_t0);  // entry nodes + look-back 3
         // ================= absolute slots, last op per slot (lane = op) =================
+        // lastk[s] = 1 + the last op of the tile whose value is stored in slot s (0 = none).  Steps run in stream order; inside a
+        // step several lanes may hold the same slot: all store, read back, and the lanes that lost to an EARLIER op store again
+        // (usually one retry).  __match_any_sync did this in one instruction but took 19 cycles per instruction of this loop.
         for (unsigned kb = 0; kb < n_ops; kb += 32u) {
             const unsigned k     = kb + lane;
-            const bool     valid = k < n_ops;
-            unsigned       s     = 64u + lane;
-            if (valid) {
+            unsigned       s     = 64u;
+            if (k < n_ops) {
                 const unsigned s8 = sm.slot[k], b = sm.base[k];
                 if (s8 < 0xC0u) {  // an OP_RUN repeats its predecessor: never the only writer of a slot
                     s = s8 & 63u;
                     if (b >= kIdE && b < kIdExt) {  // before the lane's first root: the walk knew the slot relative to the lane's entry
                         s = (s + sm.hE[b - kIdE]) & 63u;
                         if (any_idx) sm.slot[k] = (unsigned char)(s | (s8 & 0xC0u));  // the searches below compare absolute slots
+                    } else if (b == kIdAbsA) {  // a literal with the tile's entry alpha
+                        s = (s + 11u * ain) & 63u;
+                        if (any_idx) sm.slot[k] = (unsigned char)(s | (s8 & 0xC0u));
                     }
                 }
             }
-            const unsigned m = __match_any_sync(kFull, s);
-            if (s < 64u && (m & lanemask_gt(lane)) == 0) sm.lastk[s] = (unsigned short)k;
+#ifdef QB_WT_MATCH
+            const unsigned m = __match_any_sync(kFull, s < 64u ? s : 64u + lane);
+            if (s < 64u && (m & lanemask_gt(lane)) == 0) sm.lastk[s] = (unsigned short)(k + 1u);
             __syncwarp();
+#else
+            bool again = s < 64u;
+            do {
+                if (again) sm.lastk[s] = (unsigned short)(k + 1u);
+                __syncwarp();
+                again = s < 64u && sm.lastk[s] < k + 1u;
+            } while (__ballot_sync(kFull, again));
+#endif
         }
-        QB_STAMP(desc, 70, 0, qb_t0);  // slots + last writers
+        QB_STAMP(desc, 74, 0, qb_t0);  // slots + last writers
 
-        // ================= OP_INDEX: the last earlier op with the same slot =================
+        // ================= OP_INDEX ops: writers (backward search over slot[]) and pointer jumping =================
         unsigned need_lo = 0, need_hi = 0;  // table entries of the state entering the tile that are read
-        if (__ballot_sync(kFull, idxm != 0)) {
-            const unsigned* W = reinterpret_cast<const unsigned*>(sm.slot);
-            for (unsigned bits = idxm; bits; bits &= bits - 1u) {
-                const unsigned q = opbase + (unsigned)__ffs((int)bits) - 1u, s = sm.slot[q] & 63u;
-                const unsigned pat = s * 0x01010101u;
-                unsigned       found = kNoOp;
-                unsigned       keep  = (1u << (8u * (q & 3u))) - 1u;  // first word: only the ops before q
-                for (int wi = (int)(q >> 2); wi >= 0; --wi) {
-                    const unsigned wv = W[wi];
-                    const unsigned x  = (wv & 0x3F3F3F3Fu) ^ pat;                // bytes 0..0x3F, zero where the slot matches
-                    const unsigned nr = ~(wv & (wv << 1)) >> 1;                  // bit 6 of a byte: not an OP_RUN (0xC0 | run - 1)
-                    const unsigned m  = (0x40404040u - x) & 0x40404040u & keep & nr;  // no borrow crosses a byte
-                    if (m) {
-                        found = (unsigned)wi * 4u + ((31u - (unsigned)__clz((int)m)) >> 3);
-                        break;
-                    }
-                    keep = 0xFFFFFFFFu;
-                }
-                if (found != kNoOp) sm.base[q] = (unsigned short)found;
-                else {
-                    sm.base[q] = (unsigned short)(kIdExt + s);
-                    if (s < 32u) need_lo |= 1u << s;
-                    else need_hi |= 1u << (s - 32u);
-                }
-            }
-        }
-        __syncwarp();
-
-        // ================= pointer jumping over the entry nodes and the OP_INDEX ops =================
-        if (any_idx) {
-            const unsigned maxJ = __reduce_max_sync(kFull, 1u + (unsigned)__popc(idxm));
-            for (;;) {
-                bool     changed = false;
-                unsigned bits    = idxm;
-                for (unsigned i = 0; i < maxJ; ++i) {
-                    unsigned x = kNoOp;
-                    if (i == 0) x = kIdE + lane;
-                    else if (bits) x = opbase + (unsigned)__ffs((int)bits) - 1u, bits &= bits - 1u;
-                    unsigned nb = 0, nr = 0;
-                    bool     upd = false;
-                    if (x != kNoOp) {
-                        const unsigned b = sm.base[x];
-                        if (b < kIdExt) nb = sm.base[b], nr = add4(sm.rec[x], sm.rec[b]), upd = true;
-                    }
-                    __syncwarp();  // every lane has read its target before any node changes
-                    if (upd) sm.base[x] = (unsigned short)nb, sm.rec[x] = nr, changed = true;
-                    __syncwarp();
-                }
-                if (!__ballot_sync(kFull, changed)) break;
-            }
-            // entries of the incoming state the nodes end in
-            unsigned bits = idxm;
-            for (unsigned i = 0; i <= (unsigned)__popc(idxm); ++i) {
-                unsigned x = kIdE + lane;
-                if (i) x = opbase + (unsigned)__ffs((int)bits) - 1u, bits &= bits - 1u;
-                const unsigned b = sm.base[x];
-                if (b != kIdAbs && b < kIdExt + 64u) {
-                    const unsigned e = b - kIdExt;
-                    if (e < 32u) need_lo |= 1u << e;
-                    else need_hi |= 1u << (e - 32u);
-                }
-            }
-        }
-        QB_STAMP(desc, 70, 1, qb_t0);  // index search + jumping
+        if (any_idx) wt_resolve_index(sm, idxm, opbase, need_lo, need_hi);
+        QB_STAMP(desc, 74, 1, qb_t0);  // index search + jumping
 
         // ================= the tile's transfer function: entries it can state now =================
         // entry e = lane, lane + 32 (table slots) and, in lane 0, 64 (prev)
@@ -652,23 +742,26 @@ namespace qb
             const unsigned e = lane + 32u * hh;
             pub_ref[hh] = 66u, pub_add[hh] = 0;
             if (e > 64u) continue;
-            const unsigned k = e < 64u ? sm.lastk[e] : (n_ops ? n_ops - 1u : kNoOp);
+            const unsigned k = e < 64u ? (unsigned)sm.lastk[e] - 1u : n_ops - 1u;  // 0xFFFFFFFF = none
+            const bool     none = e < 64u ? sm.lastk[e] == 0 : n_ops == 0;
             unsigned       ref = e, add = 0;
-            if (k != kNoOp) {
+            if (!none) {
                 unsigned b = sm.base[k];
                 add        = sm.rec[k];
                 if (b < kIdExt) add = add4(add, sm.rec[b]), b = sm.base[b];  // one hop: entry nodes and OP_INDEX ops are final
+                if (b == kIdAbsA) add |= ain << 24, b = kIdAbs;
                 ref = b == kIdAbs ? 65u : b - kIdExt;
             }
             pub_ref[hh] = ref, pub_add[hh] = add;
             if (ref == 65u) st_word(desc + kDwState + e, pack_word(add, ST_INCL, epoch));
             else st_word(desc + kDwState + e, pack_word((uint64_t)ref << 32 | add, ST_AGG, epoch));
-            if (k != kNoOp && ref < 64u) {  // an entry this tile writes from an incoming one: resolve it, publish it inclusive below
+            if (!none && ref < 64u) {  // an entry this tile writes from an incoming one: resolve it, publish it inclusive below
                 if (ref < 32u) need_lo |= 1u << ref;
                 else need_hi |= 1u << (ref - 32u);
             }
         }
         if (tail_fill) need_lo |= 1u;  // the zero padding decodes as OP_INDEX 0
+        QB_STAMP(desc, 77, 0, qb_t0);  // transfer function
 
         // ================= look-back 4: the entries of the incoming state that are read =================
         need_lo = __reduce_or_sync(kFull, need_lo), need_hi = __reduce_or_sync(kFull, need_hi);
@@ -700,7 +793,7 @@ namespace qb
             }
         }
         __syncwarp();
-        QB_STAMP(desc, 71, 0, qb_t0);  // state look-back
+        QB_STAMP(desc, 75, 0, qb_t0);  // state look-back
 
         // ================= emit: values, verification, pixels (lane = op) =================
         bool           bad    = false;
@@ -708,15 +801,15 @@ namespace qb
         const unsigned tgt    = P.target;
         uint8_t* const obase  = out + pix_base * tgt;
         // FAST: rows top-down and (four-byte pixels) a word-aligned image; else the general store_pixel
-        auto emit = [&](auto fast_tag) {
-            constexpr bool FAST    = decltype(fast_tag)::value;
+        const bool fast = !P.flip && (tgt == 3u || (reinterpret_cast<uintptr_t>(out) & 3u) == 0);
+        {
             unsigned       carry   = prev_in;  // value of the op before this step's first one
             unsigned       xcarry  = 0;        // extra OP_RUN pixels before this step
             const unsigned* recp   = sm.rec + lane;
             const unsigned short* basep = sm.base + lane;
             const unsigned char*  slotp = sm.slot + lane;
             auto put = [&](unsigned po, unsigned val) {  // pixel `po` of this tile
-                if (!FAST) store_pixel(out, pix_base + po, val, P);
+                if (!fast) store_pixel(out, pix_base + po, val, P);
                 else if (tgt == 4u) reinterpret_cast<unsigned*>(obase)[po] = val;
                 else {
                     uint8_t* d = obase + po * 3u;
@@ -772,44 +865,10 @@ namespace qb
                     }
                 }
             }
-        };
-        if (!P.flip && (tgt == 3u || (reinterpret_cast<uintptr_t>(out) & 3u) == 0)) emit(std::true_type{});
-        else emit(std::false_type{});
-        // a refuted tile makes the image eligible for the next round, from the first such tile on
-        if (__ballot_sync(kFull, bad)) {
-            if (lane == 0) {
-                if (round == 0) atomicOr(&res->bad, 1u);
-                atomicMax(&res->first_bad[round], 0xFFFFFFFFu - t);
-                P.control->any_bad[round] = 1;
-            }
-            __syncwarp();
-            // remember the alpha seen at each refuted OP_RGB for the next round (exact if everything before it was exact)
-            const unsigned nf = min(sm.nfail, (unsigned)kFixMax);
-            for (unsigned f = 0; f < nf; ++f) {
-                const unsigned k = sm.fails[f] & 0xFFFFu, actual = sm.fails[f] >> 16;
-                if (k >= opbase && k < opbase + nops) {  // the owning lane walks to the op's byte position
-                    unsigned p = cbeg + my_entry;
-                    for (unsigned i = opbase; i < k; ++i) p += op_length(B[p]);
-                    unsigned j = 0;
-                    for (; j < sm.fixn; ++j)
-                        if ((sm.fixe[j] & 0xFFFFu) == p) break;
-#ifdef QB_EMU_TRACE
-                    if (t == 21) fprintf(stderr, "MERGE round %u f %u k %u actual %02x p %03x j %u fixn %u\n", round, f, k, actual, p, j, sm.fixn);
-#endif
-                    if (j < (unsigned)kFixMax) {
-                        sm.fixe[j] = p | actual << 16;
-                        if (j == sm.fixn) sm.fixn = j + 1u;
-                        sm.fix_dirty = 1;
-                    }
-                }
-                __syncwarp();
-            }
-            if (sm.fix_dirty && lane < (unsigned)kFixWords) {
-                const unsigned n = min(sm.fixn, (unsigned)kFixMax);
-                fix[lane] = lane == 0 ? (n | (P.epoch & 0xFFFFFFu) << 8) : (lane <= n ? sm.fixe[lane - 1] : 0u);
-            }
         }
-        QB_STAMP(desc, 71, 1, qb_t0);  // emit
+        // a refuted tile makes the image eligible for the next round, from the first such tile on
+        if (__ballot_sync(kFull, bad)) wt_record_failures(P, sm, round, res, t, fix, B, cbeg + my_entry, opbase, nops);
+        QB_STAMP(desc, 75, 1, qb_t0);  // emit
 
         // ---- the stream ended before the image: the zero padding decodes as INDEX 0 forever (simple.cpp:106,132-135)
         if (t == ntiles - 1) {
@@ -817,8 +876,8 @@ namespace qb
             if (lane == 0) res->pixels = have < N ? have : N;
             if (tail_fill) {
                 unsigned fill = sm.rec[kIdExt + 0u];  // table[0] after this tile
-                const unsigned k0 = sm.lastk[0];
-                if (k0 != kNoOp) {
+                if (sm.lastk[0]) {
+                    const unsigned k0 = sm.lastk[0] - 1u;
                     fill             = sm.rec[k0];
                     const unsigned b = sm.base[k0];
                     if (b != kIdAbs) fill = add4(fill, sm.rec[b]);
