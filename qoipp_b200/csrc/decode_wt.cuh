@@ -110,6 +110,7 @@ namespace qb
     constexpr int kDecDescWords = 72;
 #endif
     constexpr int kDwParse = 0, kDwPixA = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
+    constexpr int kDwNeedLo = 70, kDwNeedHi = 71;  // entries of the incoming state this tile read (slots 0..31 / 32..63, bit 32: prev)
     constexpr int kDwGrp = 68, kDwSup = 69;  // totals of the 64 tiles / 4096 tiles ending with this tile (see wt_gather_pixa)
     constexpr unsigned kGrp = 64, kSup = 4096;
     constexpr int kFixWords = 16, kFixMax = kFixWords - 1;  // word 0: count | decode tag << 8; entries: pos | alpha << 16
@@ -391,17 +392,23 @@ namespace qb
         }
     }
 
-    // A tile whose verification failed: flag the image for the next round and remember, for every refuted OP_RGB, the alpha
-    // it actually saw (exact if everything before it was exact).  Cold.  One warp.
-    __device__ QB_NOINLINE void wt_record_failures(const DecParams& P, WtSmem& sm, unsigned round, DecResult* res, unsigned t, uint32_t* fix,
-                                                   const unsigned char* B, unsigned first_pos, unsigned opbase, unsigned nops)
+    // A tile whose verification failed: remember, for every refuted OP_RGB, the alpha it actually saw (exact if everything
+    // before it was exact) -- in shared memory for the tile's own repair pass and in the tile's global list for the retry
+    // rounds.  Cold.  One warp.
+    // `from` = first tile the next round has to decode again (kNoRedo: none, the tile repairs itself)
+    constexpr unsigned kNoRedo = 0xFFFFFFFFu;
+    __device__ QB_NOINLINE void wt_flag_redo(const DecParams& P, unsigned round, DecResult* res, unsigned from)
     {
-        const unsigned lane = threadIdx.x & 31u;
-        if (lane == 0) {
+        if ((threadIdx.x & 31u) == 0) {
             if (round == 0) atomicOr(&res->bad, 1u);
-            atomicMax(&res->first_bad[round], 0xFFFFFFFFu - t);
+            atomicMax(&res->first_bad[round], 0xFFFFFFFFu - from);
             P.control->any_bad[round] = 1;
         }
+    }
+    __device__ QB_NOINLINE void wt_record_failures(const DecParams& P, WtSmem& sm, uint32_t* fix, const unsigned char* B, unsigned first_pos,
+                                                   unsigned opbase, unsigned nops)
+    {
+        const unsigned lane = threadIdx.x & 31u;
         __syncwarp();
         const unsigned nf = min(sm.nfail, (unsigned)kFixMax);
         for (unsigned f = 0; f < nf; ++f) {
@@ -424,6 +431,57 @@ namespace qb
             const unsigned n = min(sm.fixn, (unsigned)kFixMax);
             fix[lane] = lane == 0 ? (n | (P.epoch & 0xFFFFFFu) << 8) : (lane <= n ? sm.fixe[lane - 1] : 0u);
         }
+    }
+
+    // A tile repaired itself and some of its carry words changed.  Follow the changed state entries through the tiles behind
+    // it: a tile that read a changed entry (its kDwNeed words) must be decoded again -- flag the retry round from there; an
+    // entry a tile overwrites with a constant, or derives from an unchanged entry (the `ref` its state words keep), stops being
+    // changed.  Usually nothing read the one or two table slots in question and they are overwritten within a tile or two.
+    // A changed pixel / alpha or slot word is not followed (everything behind the tile is flagged).  Cold.  One warp.
+    __device__ QB_NOINLINE void wt_repair_scan(const DecParams& P, uint64_t* desc, unsigned t, unsigned ntiles, unsigned round, DecResult* res,
+                                               const Epochs& ep, const uint64_t (&old_word)[3])
+    {
+        constexpr unsigned kScan = 16;  // tiles followed before giving up
+        const unsigned     lane  = threadIdx.x & 31u;
+        unsigned dlo = 0, dhi = 0, dprev = 0, hard = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const unsigned wi = 1u + 32u * i + lane;
+            if (wi <= (unsigned)kDwState + 64u && ld_word(desc + wi) != old_word[i]) {
+                if (wi < (unsigned)kDwState) hard = 1;
+                else {
+                    const unsigned e = wi - kDwState;
+                    if (e < 32u) dlo |= 1u << e;
+                    else if (e < 64u) dhi |= 1u << (e - 32u);
+                    else dprev = 1;
+                }
+            }
+        }
+        dlo = __reduce_or_sync(kFull, dlo), dhi = __reduce_or_sync(kFull, dhi), dprev = __reduce_or_sync(kFull, dprev), hard = __reduce_or_sync(kFull, hard);
+        if (!(dlo | dhi | dprev | hard)) return;  // the repaired tile says exactly what it said before
+        unsigned u = t + 1u;
+        if (!hard) {
+            for (; u < ntiles && u <= t + kScan; ++u) {
+                const uint64_t* d_u = desc + (uint64_t)(u - t) * kDecDescWords;
+                const uint64_t  nl = word_payload(wait_word(d_u + kDwNeedLo, ep, u)), nh = word_payload(wait_word(d_u + kDwNeedHi, ep, u));
+                if (((unsigned)nl & dlo) | ((unsigned)nh & dhi) | dprev) break;  // tile u read a changed entry (prev is always read)
+                // what tile u hands on: an entry is still changed if it is derived from a changed one
+                bool d[3];
+#pragma unroll
+                for (int hh = 0; hh < 3; ++hh) {
+                    const unsigned e = lane + 32u * hh;
+                    d[hh]            = false;
+                    if (e <= 64u) {
+                        const unsigned ref = (unsigned)(word_payload(wait_word(d_u + kDwState + e, ep, u)) >> 32) & 0x7Fu;
+                        d[hh] = ref < 32u ? (dlo >> ref) & 1u : (ref < 64u ? (dhi >> (ref - 32u)) & 1u : (ref == 64u ? dprev != 0 : false));
+                    }
+                }
+                dlo = __ballot_sync(kFull, d[0]), dhi = __ballot_sync(kFull, d[1]), dprev = __ballot_sync(kFull, d[2]) & 1u;
+                if (!(dlo | dhi | dprev)) return;  // every changed entry has been overwritten before anything read it
+            }
+            if (u >= ntiles) return;  // the stream ended first
+        }
+        if (u < ntiles) wt_flag_redo(P, round, res, u);
     }
 
     // one tile (global ticket `gticket`) of round `round`; one warp
@@ -469,7 +527,6 @@ namespace qb
             __syncwarp();
         }
         const unsigned char* B     = sm.bytes + shift;
-        const unsigned       fixn0 = sm.fixn0;
         const unsigned       cbeg  = lane * kWtChunk;
         const unsigned       cend  = min(cbeg + (unsigned)kWtChunk, limit);  // ops of this lane start below cend
         QB_STAMP(desc, 72, 0, qb_t0);  // ticket + staging
@@ -528,6 +585,18 @@ namespace qb
         const unsigned my_entry = map_at(excl_map, tile_entry);
         QB_STAMP(desc, 72, 1, qb_t0);  // parse + look-back 1
 
+        // ---- everything from here to the emit pass may run again ("repair"): a tile whose OP_RGB alpha speculation is
+        // refuted learns the alpha it saw and decodes itself again at once.  Its carry words were published already; if the
+        // repaired tile publishes the SAME words (the wrong alpha usually dies inside the tile: the next OP_RGBA resets it and
+        // the table slots it touched are overwritten), nothing downstream changed and no retry round is needed.  One refuted
+        // op in 18 000 tiles (RGBA photo with soft alpha blobs) used to cost a second decode of everything behind it.
+        constexpr unsigned kRepairPasses = 3;
+        uint64_t           old_word[3] = { 0, 0, 0 };  // this lane's share of words 1 .. 67 as first published
+        uint64_t           pix_base_f = 0;
+        unsigned           n_pix_f = 0, fixn0 = sm.fixn0;
+        bool               tail_fill_f = false, still_bad = false;
+        unsigned           pass = 0;
+        for (;; ++pass) {
         // ================= counts of the true path, look-back 2: pixels and inherited alpha =================
         unsigned nops, npx_lane, a_sum;  // a_sum: 0x100 | alpha after this lane's last alpha setter, 0 = none
         {
@@ -639,7 +708,7 @@ namespace qb
             const unsigned last_lane = 31u - (unsigned)__clz((int)(__ballot_sync(kFull, nops != 0) | 1u));
             const unsigned lb = __shfl_sync(kFull, exit_bid, (int)last_lane), lr = __shfl_sync(kFull, exit_rec, (int)last_lane);
             prev_done = n_ops != 0 && lb == kIdAbs;
-            if (prev_done && lane == 0) st_word(desc + kDwState + 64, pack_word(lr, ST_INCL, epoch));
+            if (prev_done && lane == 0) st_word(desc + kDwState + 64, pack_word((uint64_t)65u << 32 | lr, ST_INCL, epoch));
         }
         // entry nodes: the value entering lane l's chunk = the value of the op before its first one
         if (any_idx) {  // general form: an alias of that op, resolved by the pointer jumping below
@@ -753,7 +822,7 @@ namespace qb
                 ref = b == kIdAbs ? 65u : b - kIdExt;
             }
             pub_ref[hh] = ref, pub_add[hh] = add;
-            if (ref == 65u) st_word(desc + kDwState + e, pack_word(add, ST_INCL, epoch));
+            if (ref == 65u) st_word(desc + kDwState + e, pack_word((uint64_t)65u << 32 | add, ST_INCL, epoch));
             else st_word(desc + kDwState + e, pack_word((uint64_t)ref << 32 | add, ST_AGG, epoch));
             if (!none && ref < 64u) {  // an entry this tile writes from an incoming one: resolve it, publish it inclusive below
                 if (ref < 32u) need_lo |= 1u << ref;
@@ -765,6 +834,10 @@ namespace qb
 
         // ================= look-back 4: the entries of the incoming state that are read =================
         need_lo = __reduce_or_sync(kFull, need_lo), need_hi = __reduce_or_sync(kFull, need_hi);
+        if (lane == 0) {  // what this tile reads of its predecessors' state: lets a repaired predecessor tell whether it mattered
+            st_word(desc + kDwNeedLo, pack_word(need_lo, ST_INCL, epoch));
+            st_word(desc + kDwNeedHi, pack_word((uint64_t)1u << 32 | need_hi, ST_INCL, epoch));
+        }
         if ((need_lo >> lane) & 1u) sm.rec[kIdExt + lane] = wt_resolve_entry(desc, t, lane, ep);
         if ((need_hi >> lane) & 1u) sm.rec[kIdExt + 32u + lane] = wt_resolve_entry(desc, t, lane + 32u, ep);
         if (lane == 0) sm.rec[kIdExt + 64u] = wt_resolve_entry(desc, t, 64u, ep);  // prev: nearly every tile reads it
@@ -778,7 +851,7 @@ namespace qb
                 const bool known = pub_ref[hh] == 64u || ((pub_ref[hh] < 32u ? need_lo >> pub_ref[hh] : need_hi >> (pub_ref[hh] - 32u)) & 1u);
                 if (known) {
                     pub_add[hh] = add4(pub_add[hh], sm.rec[kIdExt + pub_ref[hh]]);
-                    st_word(desc + kDwState + e, pack_word(pub_add[hh], ST_INCL, epoch));
+                    st_word(desc + kDwState + e, pack_word((uint64_t)pub_ref[hh] << 32 | pub_add[hh], ST_INCL, epoch));  // value; the entry it came from stays readable
                 }
             }
         }
@@ -866,15 +939,34 @@ namespace qb
                 }
             }
         }
-        // a refuted tile makes the image eligible for the next round, from the first such tile on
-        if (__ballot_sync(kFull, bad)) wt_record_failures(P, sm, round, res, t, fix, B, cbeg + my_entry, opbase, nops);
+        pix_base_f = pix_base, n_pix_f = n_pix, tail_fill_f = tail_fill;
+        still_bad  = __ballot_sync(kFull, bad) != 0;
+        if (!still_bad) break;
+        const unsigned nfail = sm.nfail;  // refuted OP_RGB ops (an OP_INDEX that read a never-written slot counts in `bad` only)
+        if (nfail) wt_record_failures(P, sm, fix, B, cbeg + my_entry, opbase, nops);
+        if (nfail == 0 || pass + 1u >= kRepairPasses) break;  // nothing learned, or not converging: the retry rounds take over
+        if (pass == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (1u + 32u * i + lane <= (unsigned)kDwState + 64u) old_word[i] = ld_word(desc + 1 + 32 * i + lane);
+        }
+        __syncwarp();
+        fixn0 = sm.fixn;
+        if (lane == 0) sm.fixn0 = fixn0, sm.nfail = 0;
+        __syncwarp();
+        }  // repair loop
+        if (still_bad) {
+            wt_flag_redo(P, round, res, t);  // the image is eligible for the next round, from this tile on
+        } else if (pass) {  // repaired: did anything this tile told the others change, and did it matter?
+            wt_repair_scan(P, desc, t, ntiles, round, res, ep, old_word);
+        }
         QB_STAMP(desc, 75, 1, qb_t0);  // emit
 
         // ---- the stream ended before the image: the zero padding decodes as INDEX 0 forever (simple.cpp:106,132-135)
         if (t == ntiles - 1) {
-            const uint64_t have = pix_base + n_pix;
+            const uint64_t have = pix_base_f + n_pix_f;
             if (lane == 0) res->pixels = have < N ? have : N;
-            if (tail_fill) {
+            if (tail_fill_f) {
                 unsigned fill = sm.rec[kIdExt + 0u];  // table[0] after this tile
                 if (sm.lastk[0]) {
                     const unsigned k0 = sm.lastk[0] - 1u;
