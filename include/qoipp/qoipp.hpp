@@ -330,6 +330,16 @@ namespace qoipp
         Pixel                                   m_prev;
         PixelArr<constants::running_array_size> m_seen;
     };
+
+    // ---- extension of the B200 backend (not in the reference): GPU selection.  Every host thread owns one device context
+    // per GPU it uses.  The GPU of a call is, in this order: set_device() of the calling thread, the environment variable
+    // QOIPP_B200_DEVICE, the thread's current CUDA device (cudaGetDevice, 0 unless the application changed it).
+    namespace b200
+    {
+        void set_device(int device) noexcept;  // < 0: back to the default rule
+        int  device() noexcept;
+        int  device_count() noexcept;
+    }
 }
 
 #endif

@@ -51,6 +51,7 @@ typedef struct qoipp_b200_ctx qoipp_b200_ctx;
 int32_t     qoipp_b200_version(void);
 const char* qoipp_b200_error_string(int32_t code); /* qoipp::to_string(Error), common.hpp:260-280 */
 int32_t     qoipp_b200_device_count(void);
+int32_t     qoipp_b200_current_device(void); /* cudaGetDevice of the calling thread (0 when there is none) */
 
 int32_t qoipp_b200_ctx_create(int32_t device, qoipp_b200_ctx** out);
 int32_t qoipp_b200_ctx_destroy(qoipp_b200_ctx* ctx);
@@ -80,6 +81,11 @@ int32_t qoipp_b200_encode_batch_dev(qoipp_b200_ctx* ctx, const uint8_t* d_raw, u
                                     const qoipp_b200_desc* desc, uint8_t* d_out, uint64_t out_stride, uint64_t out_cap,
                                     uint64_t* d_written, void* stream);
 
+/* same, host buffers (page-locked buffers are used in place; h_written[k] may be NULL); returns when the outputs are in h_out */
+int32_t qoipp_b200_encode_batch_host(qoipp_b200_ctx* ctx, const uint8_t* h_raw, uint64_t raw_stride, uint32_t n_images,
+                                     const qoipp_b200_desc* desc, uint8_t* h_out, uint64_t out_stride, uint64_t out_cap,
+                                     uint64_t* h_written);
+
 /* ---- resumable encode: replaces StreamEncoder::encode (source/stream.cpp:138-239).  `state` is carried by the
  * caller between calls; in_size is truncated to whole pixels (stream.cpp:59). */
 int32_t qoipp_b200_stream_encode_host(qoipp_b200_ctx* ctx, qoipp_b200_state* state, const uint8_t* h_in, uint64_t in_size,
@@ -93,8 +99,11 @@ int32_t qoipp_b200_decode_dev(qoipp_b200_ctx* ctx, const uint8_t* d_qoi, uint64_
                               uint8_t target_channels, int32_t flip_vertically, uint8_t* d_out, uint64_t out_cap,
                               void* stream);
 /* 0 when the last decode on this context completed; *path: 0 = verified in round 0, 1..4 = retry rounds used,
- * + 100 = the sequential loop produced part of the image, + 1000 = the thread-serial fast path was refuted first */
+ * + 100 = the sequential loop produced part of the image */
 int32_t qoipp_b200_decode_status(qoipp_b200_ctx* ctx, void* stream, int32_t* path);
+
+/* same for the last batch decode: paths[k] of image k (n_images as given to the batch call) */
+int32_t qoipp_b200_decode_status_batch(qoipp_b200_ctx* ctx, void* stream, int32_t* paths, uint32_t n_images);
 
 int32_t qoipp_b200_decode_host(qoipp_b200_ctx* ctx, const uint8_t* h_qoi, uint64_t qoi_size, uint8_t target_channels,
                                int32_t flip_vertically, uint8_t* h_out, uint64_t out_cap, qoipp_b200_desc* desc);
@@ -104,6 +113,16 @@ int32_t qoipp_b200_decode_host(qoipp_b200_ctx* ctx, const uint8_t* h_qoi, uint64
 int32_t qoipp_b200_decode_batch_dev(qoipp_b200_ctx* ctx, const uint8_t* d_qoi, const uint64_t* h_offsets, uint32_t n_images,
                                     const qoipp_b200_desc* desc, uint8_t target_channels, uint8_t* d_out,
                                     uint64_t out_stride, void* stream);
+
+/* same with stream k at d_qoi + k*in_stride, h_sizes[k] bytes long: the layout qoipp_b200_encode_batch_dev writes
+ * (out_stride, d_written), so an encoded batch is decoded where it lies */
+int32_t qoipp_b200_decode_batch_strided_dev(qoipp_b200_ctx* ctx, const uint8_t* d_qoi, uint64_t in_stride, const uint64_t* h_sizes,
+                                            uint32_t n_images, const qoipp_b200_desc* desc, uint8_t target_channels, uint8_t* d_out,
+                                            uint64_t out_stride, void* stream);
+/* host buffers (page-locked ones are used in place); returns when the pixels are in h_out */
+int32_t qoipp_b200_decode_batch_host(qoipp_b200_ctx* ctx, const uint8_t* h_qoi, uint64_t in_stride, const uint64_t* h_sizes,
+                                     uint32_t n_images, const qoipp_b200_desc* desc, uint8_t target_channels, uint8_t* h_out,
+                                     uint64_t out_stride);
 
 /* ---- resumable decode: replaces StreamDecoder::decode / drain_run (source/stream.cpp:312-447). */
 int32_t qoipp_b200_stream_decode_host(qoipp_b200_ctx* ctx, qoipp_b200_state* state, const uint8_t* h_in, uint64_t in_size,

@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libqoipp_ref.so")
+REF_SO_V4 = os.path.join(HERE, "_ref", "libqoipp_ref_v4.so")  # same sources, -march=x86-64-v4 (bench only, AVX-512 hosts)
 
 ERROR_NAMES = {
     0: "Ok", 1: "Empty", 2: "TooShort", 3: "TooBig", 4: "NotQoi", 5: "InvalidDesc", 6: "MismatchedDesc",
@@ -242,8 +243,46 @@ class Ref:
             L.ref_sdec_initialize.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint8, u32p]
             L.ref_sdec_decode.argtypes = [C.c_void_p, u8p, C.c_uint64, u8p, C.c_uint64, u64p, u64p]
             L.ref_sdec_drain_run.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p]
+            cls._bind_bench(L)
             cls._lib = L
         return cls._lib
+
+    @staticmethod
+    def _bind_bench(L):
+        L.ref_bench.argtypes = [C.POINTER(u8p), C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint8, C.c_uint8, C.c_int, C.c_int,
+                                C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+
+    _bench_lib = None
+
+    @classmethod
+    def bench_lib(cls):
+        """Library for the timed CPU baseline: the x86-64-v4 build when this host has AVX-512, else the portable one."""
+        if cls._bench_lib is None:
+            so, march = REF_SO, "x86-64-v3"
+            try:
+                flags = next(ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")).split()
+                if os.path.exists(REF_SO_V4) and all(f in flags for f in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl")):
+                    so, march = REF_SO_V4, "x86-64-v4"
+            except Exception:
+                pass
+            L = C.CDLL(so)
+            cls._bind_bench(L)
+            cls._bench_lib = (L, march)
+        return cls._bench_lib
+
+    @classmethod
+    def bench(cls, images, w, h, ch, cs=0, threads=0, warmups=3, reps=5):
+        """The reference's own benchmark method (example/source/04_bench.cpp:445-510,733-754) on `images` (list of raw arrays):
+        encode_into a pre-allocated, pre-touched worst_size buffer and decode_into a pre-allocated buffer, thread-per-image.
+        Returns dict(enc_s, dec_s, enc_bytes, threads, march): seconds for `reps` passes over all images per direction."""
+        L, march = cls.bench_lib()
+        imgs = [_as_u8(i) for i in images]
+        arr = (u8p * len(imgs))(*[_ptr(i) for i in imgs])
+        es, ds, nb, tu = C.c_double(0), C.c_double(0), C.c_uint64(0), C.c_int(0)
+        e = L.ref_bench(arr, len(imgs), imgs[0].size, w, h, ch, cs, threads, warmups, reps, C.byref(es), C.byref(ds), C.byref(nb), C.byref(tu))
+        if e != 0:
+            raise RuntimeError(f"ref_bench failed: {e}")
+        return {"enc_s": es.value, "dec_s": ds.value, "enc_bytes": nb.value, "threads": tu.value, "march": march}
 
     @classmethod
     def worst_size(cls, w, h, ch, cs=0):

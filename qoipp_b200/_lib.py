@@ -44,6 +44,7 @@ def _load():
         "qoipp_b200_version": (C.c_int32, []),
         "qoipp_b200_error_string": (C.c_char_p, [C.c_int32]),
         "qoipp_b200_device_count": (C.c_int32, []),
+        "qoipp_b200_current_device": (C.c_int32, []),
         "qoipp_b200_ctx_create": (C.c_int32, [C.c_int32, pp]),
         "qoipp_b200_ctx_destroy": (C.c_int32, [vp]),
         "qoipp_b200_count_bytes": (C.c_int32, [dp, u64p]),
@@ -53,9 +54,13 @@ def _load():
         "qoipp_b200_encode_status": (C.c_int32, [vp, vp, u64p, i32p]),
         "qoipp_b200_encode_host": (C.c_int32, [vp, vp, C.c_uint64, dp, vp, C.c_uint64, u64p, i32p]),
         "qoipp_b200_encode_batch_dev": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, dp, vp, C.c_uint64, C.c_uint64, vp, vp]),
+        "qoipp_b200_encode_batch_host": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, dp, vp, C.c_uint64, C.c_uint64, u64p]),
+        "qoipp_b200_decode_batch_strided_dev": (C.c_int32, [vp, vp, C.c_uint64, u64p, C.c_uint32, dp, C.c_uint8, vp, C.c_uint64, vp]),
+        "qoipp_b200_decode_batch_host": (C.c_int32, [vp, vp, C.c_uint64, u64p, C.c_uint32, dp, C.c_uint8, vp, C.c_uint64]),
         "qoipp_b200_stream_encode_host": (C.c_int32, [vp, C.POINTER(State), vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]),
         "qoipp_b200_decode_dev": (C.c_int32, [vp, vp, C.c_uint64, dp, C.c_uint8, C.c_int32, vp, C.c_uint64, vp]),
         "qoipp_b200_decode_status": (C.c_int32, [vp, vp, i32p]),
+        "qoipp_b200_decode_status_batch": (C.c_int32, [vp, vp, i32p, C.c_uint32]),
         "qoipp_b200_decode_host": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint8, C.c_int32, vp, C.c_uint64, dp]),
         "qoipp_b200_decode_batch_dev": (C.c_int32, [vp, vp, u64p, C.c_uint32, dp, C.c_uint8, vp, C.c_uint64, vp]),
         "qoipp_b200_stream_decode_host": (C.c_int32, [vp, C.POINTER(State), vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]),

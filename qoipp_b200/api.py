@@ -137,6 +137,13 @@ class Context:
             raise QoiError(e)
         return path.value
 
+    def decode_status_batch(self, n_images: int, stream=0) -> np.ndarray:
+        paths = np.zeros(n_images, dtype=np.int32)
+        e = lib.qoipp_b200_decode_status_batch(self._h, C.c_void_p(stream), paths.ctypes.data_as(C.POINTER(C.c_int32)), n_images)
+        if e:
+            raise QoiError(e)
+        return paths
+
     def decode_batch_dev(self, d_qoi, offsets: np.ndarray, w, h, ch, cs, target, d_out, out_stride, stream=0):
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         e = lib.qoipp_b200_decode_batch_dev(self._h, _dev_ptr(d_qoi), offsets.ctypes.data_as(C.POINTER(C.c_uint64)), offsets.size - 1,

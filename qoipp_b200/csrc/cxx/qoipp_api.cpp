@@ -6,10 +6,12 @@
 
 #include "qoipp_b200.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <new>
 #include <sstream>
+#include <vector>
 
 namespace fs = std::filesystem;
 
@@ -17,21 +19,53 @@ namespace
 {
     using namespace qoipp;
 
-    // one device context per host thread: concurrent callers never share a stream or a workspace
+    // one device context per host thread AND device: concurrent callers never share a stream or a workspace.  The device
+    // is the one the calling thread selected (qoipp::b200::set_device, else QOIPP_B200_DEVICE, else the thread's current
+    // CUDA device), so a thread-per-GPU consumer of qoipp::encode / decode reaches every GPU of the box.
     struct ThreadCtx {
         qoipp_b200_ctx* ctx  = nullptr;
         int32_t         code = 0;
-        ThreadCtx() { code = qoipp_b200_ctx_create(0, &ctx); }
-        ~ThreadCtx()
+        int             device = -1;
+    };
+
+    thread_local int tl_device = -1;  // qoipp::b200::set_device
+
+    int env_device()
+    {
+        static const int v = [] {
+            const char* e = std::getenv("QOIPP_B200_DEVICE");
+            return e && *e ? std::atoi(e) : -1;
+        }();
+        return v;
+    }
+
+    int wanted_device()
+    {
+        if (tl_device >= 0) return tl_device;
+        if (env_device() >= 0) return env_device();
+        return qoipp_b200_current_device();
+    }
+
+    struct ThreadCtxSet {
+        std::vector<ThreadCtx> all;
+        ~ThreadCtxSet()
         {
-            if (ctx) qoipp_b200_ctx_destroy(ctx);
+            for (auto& t : all)
+                if (t.ctx) qoipp_b200_ctx_destroy(t.ctx);
         }
     };
 
     ThreadCtx& thread_ctx()
     {
-        thread_local ThreadCtx t;
-        return t;
+        thread_local ThreadCtxSet set;
+        const int                 dev = wanted_device();
+        for (auto& t : set.all)
+            if (t.device == dev) return t;
+        ThreadCtx t;
+        t.device = dev;
+        t.code   = qoipp_b200_ctx_create(dev, &t.ctx);
+        set.all.push_back(t);
+        return set.all.back();
     }
 
     // C ABI code -> qoipp::Error (the enum has no device member: CUDA failures surface as IoError)
@@ -453,4 +487,12 @@ namespace qoipp
         m_prev = start_pixel;
         m_seen.fill(Pixel{});
     }
+}
+
+// ---- extension (not in the reference): which GPU serves the calling thread
+namespace qoipp::b200
+{
+    void set_device(int device) noexcept { tl_device = device; }
+    int  device() noexcept { return wanted_device(); }
+    int  device_count() noexcept { return qoipp_b200_device_count(); }
 }

@@ -33,6 +33,60 @@ namespace
                                             kWtSmemBytes, s));
         return 0;
     }
+
+    // batch decode: stream k is d_qoi[start(k), start(k) + size(k))
+    template <class Span>
+    int32_t decode_batch_impl(qoipp_b200_ctx* c, const uint8_t* d_qoi, uint32_t n_images, Span span, const qoipp_b200_desc* desc,
+                                     uint8_t target, uint8_t* d_out, uint64_t out_stride, cudaStream_t s)
+    {
+        if (n_images == 0) return H::Empty;
+        uint64_t raw;
+        if (int32_t e = H::count_bytes(*desc, &raw)) return e;
+        const unsigned tgt = target ? target : desc->channels;
+        if (tgt != 3 && tgt != 4) return H::InvalidDesc;
+        const uint64_t n = (uint64_t)desc->width * desc->height;
+        if (out_stride < n * tgt) return H::NotEnoughSpace;
+        Guard g(c->device);
+        // per-image table: {first byte, one past the last} (u64 pairs) then first-tile ids (u32).  The table is built in
+        // ordinary host memory and compared with the one the device already holds: a repeated decode of the same batch
+        // layout (the steady state of a pipeline, and of bench.py) uploads nothing and does not touch the stream.  A new
+        // layout is staged through pinned memory; only then the stream is drained first (the pinned copy of the previous
+        // table may be in flight).
+        const size_t off_bytes = sizeof(uint64_t) * 2 * (size_t)n_images, tf_bytes = sizeof(uint32_t) * ((size_t)n_images + 2);
+        std::vector<uint64_t>& tab = c->batch_table;
+        tab.assign((off_bytes + tf_bytes + 7) / 8, 0);
+        auto*    ho = tab.data();
+        auto*    ht = reinterpret_cast<uint32_t*>(ho + 2 * (size_t)n_images);
+        uint64_t tiles = 0;
+        for (uint32_t k = 0; k < n_images; ++k) {
+            uint64_t start, sz;
+            span(k, start, sz);
+            if (sz <= H::kHeaderSize + H::kMarkerSize) return sz == 0 ? H::Empty : H::TooShort;
+            ho[2 * k] = start, ho[2 * k + 1] = start + sz, ht[k] = (uint32_t)tiles;
+            tiles += (sz - H::kHeaderSize + kDecTB - 1) / kDecTB;
+            if (tiles >= (1ull << 31)) return H::TooBig;
+        }
+        ht[n_images] = (uint32_t)tiles;
+        const bool same = c->batch_table_dev_bytes == off_bytes + tf_bytes && c->batch_table_stream == s && c->aux.p && c->h_pin_in.p &&
+                          std::memcmp(c->h_pin_in.p, ho, off_bytes + tf_bytes) == 0;
+        if (!same) {
+            c->batch_table_dev_bytes = 0;
+            QB_CUDA(cudaStreamSynchronize(s));
+            QB_CUDA(c->h_pin_in.reserve(off_bytes + tf_bytes));
+            QB_CUDA(c->aux.reserve(off_bytes + tf_bytes, s));
+            std::memcpy(c->h_pin_in.p, ho, off_bytes + tf_bytes);
+            QB_CUDA(cudaMemcpyAsync(c->aux.p, c->h_pin_in.p, off_bytes + tf_bytes, cudaMemcpyHostToDevice, s));
+            c->batch_table_dev_bytes = off_bytes + tf_bytes, c->batch_table_stream = s;
+        }
+        DecParams P{};
+        P.qoi = d_qoi;
+        P.offsets    = static_cast<uint64_t*>(c->aux.p);
+        P.tile_first = reinterpret_cast<uint32_t*>(static_cast<uint64_t*>(c->aux.p) + 2 * (size_t)n_images);
+        P.out = d_out, P.out_stride = out_stride, P.n_pixels = n;
+        P.width = desc->width, P.height = desc->height, P.target = tgt, P.flip = 0;
+        P.n_images = n_images, P.n_tiles = (uint32_t)tiles;
+        return launch_decode(c, P, s);
+    }
 }
 
 extern "C"
@@ -68,6 +122,19 @@ extern "C"
         QB_CUDA(cudaMemcpyAsync(h, static_cast<uint8_t*>(c->results.p) + kCtrlBytes, 64, cudaMemcpyDeviceToHost, s));
         QB_CUDA(cudaStreamSynchronize(s));
         if (path) *path = (int32_t)h->path;
+        return 0;
+    }
+
+    int32_t qoipp_b200_decode_status_batch(qoipp_b200_ctx* c, void* stream, int32_t* paths, uint32_t n_images)
+    {
+        Guard g(c->device);
+        auto  s = static_cast<cudaStream_t>(stream);
+        QB_CUDA(c->h_pin_out.reserve(sizeof(uint32_t) * (size_t)n_images));
+        // DecResult[k].path -> a packed pinned array
+        QB_CUDA(cudaMemcpy2DAsync(c->h_pin_out.p, sizeof(uint32_t), static_cast<uint8_t*>(c->results.p) + kCtrlBytes + offsetof(DecResult, path),
+                                  sizeof(DecResult), sizeof(uint32_t), n_images, cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        std::memcpy(paths, c->h_pin_out.p, sizeof(uint32_t) * (size_t)n_images);
         return 0;
     }
 
@@ -109,40 +176,52 @@ extern "C"
                                         const qoipp_b200_desc* desc, uint8_t target, uint8_t* d_out, uint64_t out_stride,
                                         void* stream)
     {
+        return decode_batch_impl(
+            c, d_qoi, n_images,
+            [&](uint32_t k, uint64_t& start, uint64_t& sz) { start = h_offsets[k], sz = h_offsets[k + 1] >= h_offsets[k] ? h_offsets[k + 1] - h_offsets[k] : 0; },
+            desc, target, d_out, out_stride, static_cast<cudaStream_t>(stream));
+    }
+
+    int32_t qoipp_b200_decode_batch_strided_dev(qoipp_b200_ctx* c, const uint8_t* d_qoi, uint64_t in_stride, const uint64_t* h_sizes,
+                                                uint32_t n_images, const qoipp_b200_desc* desc, uint8_t target, uint8_t* d_out,
+                                                uint64_t out_stride, void* stream)
+    {
+        return decode_batch_impl(
+            c, d_qoi, n_images, [&](uint32_t k, uint64_t& start, uint64_t& sz) { start = (uint64_t)k * in_stride, sz = std::min(h_sizes[k], in_stride); }, desc,
+            target, d_out, out_stride, static_cast<cudaStream_t>(stream));
+    }
+
+    int32_t qoipp_b200_decode_batch_host(qoipp_b200_ctx* c, const uint8_t* h_qoi, uint64_t in_stride, const uint64_t* h_sizes, uint32_t n_images,
+                                         const qoipp_b200_desc* desc, uint8_t target, uint8_t* h_out, uint64_t out_stride)
+    {
         if (n_images == 0) return H::Empty;
         uint64_t raw;
         if (int32_t e = H::count_bytes(*desc, &raw)) return e;
-        const unsigned tgt = target ? target : desc->channels;
+        const unsigned tgt  = target ? target : desc->channels;
         if (tgt != 3 && tgt != 4) return H::InvalidDesc;
-        const uint64_t n = (uint64_t)desc->width * desc->height;
-        if (out_stride < n * tgt) return H::NotEnoughSpace;
-        Guard g(c->device);
-        auto  s = static_cast<cudaStream_t>(stream);
-        // per-image tile ranges: offsets (u64) then first-tile ids (u32), staged through pinned memory
-        const size_t off_bytes = sizeof(uint64_t) * (n_images + 1), tf_bytes = sizeof(uint32_t) * (n_images + 2);
-        QB_CUDA(c->h_pin_in.reserve(off_bytes + tf_bytes));
-        QB_CUDA(c->aux.reserve(off_bytes + tf_bytes, s));
-        QB_CUDA(cudaStreamSynchronize(s));  // the pinned table of an earlier call may still be in flight
-        auto*    ho = static_cast<uint64_t*>(c->h_pin_in.p);
-        auto*    ht = reinterpret_cast<uint32_t*>(ho + n_images + 1);
-        uint64_t tiles = 0;
-        for (uint32_t k = 0; k < n_images; ++k) {
-            const uint64_t sz = h_offsets[k + 1] - h_offsets[k];
-            if (sz <= H::kHeaderSize + H::kMarkerSize) return H::TooShort;
-            ho[k] = h_offsets[k], ht[k] = (uint32_t)tiles;
-            tiles += (sz - H::kHeaderSize + kDecTB - 1) / kDecTB;
-            if (tiles >= (1ull << 31)) return H::TooBig;
+        const uint64_t need = (uint64_t)desc->width * desc->height * tgt;
+        if (out_stride < need) return H::NotEnoughSpace;
+        Guard          g(c->device);
+        cudaStream_t   s     = c->own_stream;
+        const uint64_t out_bytes = out_stride * (n_images - 1) + need;
+        const uint8_t* d_in  = mapped_host(h_qoi);
+        uint8_t*       d_out = mapped_host(h_out);
+        if (!d_in) {  // only the bytes of each stream travel
+            QB_CUDA(c->stage_in.reserve(in_stride * n_images + 64, s));
+            for (uint32_t k = 0; k < n_images; ++k)
+                QB_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(c->stage_in.p) + k * in_stride, h_qoi + k * in_stride, std::min(h_sizes[k], in_stride),
+                                        cudaMemcpyHostToDevice, s));
+            d_in = static_cast<uint8_t*>(c->stage_in.p);
         }
-        ho[n_images] = h_offsets[n_images], ht[n_images] = (uint32_t)tiles;
-        QB_CUDA(cudaMemcpyAsync(c->aux.p, ho, off_bytes + tf_bytes, cudaMemcpyHostToDevice, s));
-        DecParams P{};
-        P.qoi = d_qoi;
-        P.offsets    = static_cast<uint64_t*>(c->aux.p);
-        P.tile_first = reinterpret_cast<uint32_t*>(static_cast<uint64_t*>(c->aux.p) + n_images + 1);
-        P.out = d_out, P.out_stride = out_stride, P.n_pixels = n;
-        P.width = desc->width, P.height = desc->height, P.target = tgt, P.flip = 0;
-        P.n_images = n_images, P.n_tiles = (uint32_t)tiles;
-        return launch_decode(c, P, s);
+        const bool staged_out = d_out == nullptr;
+        if (staged_out) {
+            QB_CUDA(c->stage_out.reserve(out_bytes + 64, s));
+            d_out = static_cast<uint8_t*>(c->stage_out.p);
+        }
+        if (int32_t e = qoipp_b200_decode_batch_strided_dev(c, d_in, in_stride, h_sizes, n_images, desc, (uint8_t)tgt, d_out, out_stride, s)) return e;
+        if (staged_out) QB_CUDA(device_to_pageable(c, h_out, c->stage_out.p, out_bytes, s));
+        else QB_CUDA(cudaStreamSynchronize(s));
+        return 0;
     }
 
     int32_t qoipp_b200_stream_decode_host(qoipp_b200_ctx* c, qoipp_b200_state* st, const uint8_t* h_in, uint64_t in_size,

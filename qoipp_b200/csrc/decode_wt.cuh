@@ -70,7 +70,7 @@ namespace qb
 
     struct DecParams {
         const uint8_t*  qoi;
-        const uint64_t* offsets;     // [n_images + 1] device; null => single[]
+        const uint64_t* offsets;     // [n_images][2] device: first byte of stream k, one past its last; null => single[]
         const uint32_t* tile_first;  // [n_images + 1] device; null => single image
         uint64_t        single[2];
         uint8_t*        out;
@@ -234,8 +234,8 @@ namespace qb
         img    = lo;
         const unsigned f = __ldg(P.tile_first + lo);
         t = gt - f, ntiles = __ldg(P.tile_first + lo + 1) - f;
-        const uint64_t o0 = __ldg(P.offsets + lo);
-        stream = P.qoi + o0, size = __ldg(P.offsets + lo + 1) - o0;
+        const uint64_t o0 = __ldg(P.offsets + 2u * lo);
+        stream = P.qoi + o0, size = __ldg(P.offsets + 2u * lo + 1u) - o0;
     }
 
     // ---- pixels before tile t of its image and the alpha of the last OP_RGBA before it, WITHOUT a chain: every tile
@@ -1047,7 +1047,7 @@ namespace qb
         uint64_t       size;
         unsigned       first_tile = 0;
         if (P.tile_first == nullptr) stream = P.qoi + P.single[0], size = P.single[1] - P.single[0];
-        else stream = P.qoi + P.offsets[img], size = P.offsets[img + 1] - P.offsets[img], first_tile = P.tile_first[img];
+        else stream = P.qoi + P.offsets[2u * img], size = P.offsets[2u * img + 1u] - P.offsets[2u * img], first_tile = P.tile_first[img];
         uint8_t*       out   = P.out + (uint64_t)img * (S.mode == 0 ? P.out_stride : 0);
         const uint8_t* body  = S.mode == 0 ? stream + kHeader : stream;
         const uint64_t blen  = S.mode == 0 ? size - kHeader : S.in_size;

@@ -179,6 +179,9 @@ struct qoipp_b200_ctx {
     DevBuf   stage_in, stage_out;  // device staging of the host-pointer calls
     PinnedBuf h_result;   // pinned landing zone for result structs
     PinnedBuf h_pin_in, h_pin_out;
+    std::vector<uint64_t> batch_table;      // decode_batch_dev: the offset / first-tile table of this call (host)
+    cudaStream_t batch_table_stream = nullptr;  // the stream that upload was ordered on
+    size_t   batch_table_dev_bytes = 0;     // bytes of the table `aux` holds (a copy of it stays in h_pin_in), 0 = none
     PinnedBuf ring;              // page-locked ring of the pageable staging pipeline (2 slots)
     cudaEvent_t ring_ev[2] = { nullptr, nullptr };
     CopyPool* pool = nullptr;    // created with the first large pageable transfer
@@ -416,6 +419,16 @@ extern "C"
         return n;
     }
 
+    int32_t qoipp_b200_current_device(void)
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return 0;
+        }
+        return d;
+    }
+
     int32_t qoipp_b200_count_bytes(const qoipp_b200_desc* desc, uint64_t* out) { return H::count_bytes(*desc, out); }
     int32_t qoipp_b200_worst_size(const qoipp_b200_desc* desc, uint64_t* out) { return H::worst_size(*desc, out); }
     int32_t qoipp_b200_read_header(const uint8_t* h_qoi, uint64_t size, qoipp_b200_desc* out) { return H::read_header(h_qoi, size, out); }
@@ -554,6 +567,53 @@ extern "C"
         if (d_written)  // EncResult[k].written -> d_written[k]
             QB_CUDA(cudaMemcpy2DAsync(d_written, sizeof(uint64_t), c->results.p, sizeof(EncResult), sizeof(uint64_t), n_images,
                                       cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+
+    int32_t qoipp_b200_encode_batch_host(qoipp_b200_ctx* c, const uint8_t* h_raw, uint64_t raw_stride, uint32_t n_images,
+                                         const qoipp_b200_desc* desc, uint8_t* h_out, uint64_t out_stride, uint64_t out_cap,
+                                         uint64_t* h_written)
+    {
+        uint64_t raw, worst;
+        if (int32_t e = H::count_bytes(*desc, &raw)) return e;
+        if (n_images == 0) return H::Empty;
+        if (raw_stride < raw || out_stride < out_cap) return H::MismatchedDesc;
+        if (out_cap < H::kHeaderSize) return H::NotEnoughSpace;
+        H::worst_size(*desc, &worst);
+        const uint64_t cap = std::min(out_cap, worst);
+        Guard          g(c->device);
+        cudaStream_t   s     = c->own_stream;
+        const uint8_t* d_in  = mapped_host(h_raw);
+        uint8_t*       d_out = mapped_host(h_out);
+        const uint64_t in_bytes = raw_stride * (n_images - 1) + raw, out_bytes = out_stride * (n_images - 1) + cap;
+        const bool     in_place = d_in != nullptr || d_out != nullptr;  // a kernel touches host memory directly
+        if (!d_in) {
+            QB_CUDA(c->stage_in.reserve(in_bytes + 16, s));
+            QB_CUDA(pageable_to_device(c, c->stage_in.p, h_raw, in_bytes, s));
+            d_in = static_cast<uint8_t*>(c->stage_in.p);
+        }
+        const bool staged_out = d_out == nullptr;
+        if (staged_out) {
+            QB_CUDA(c->stage_out.reserve(out_bytes + 16, s));
+            d_out = static_cast<uint8_t*>(c->stage_out.p);
+        }
+        uint8_t hdr[14];
+        H::write_header(*desc, hdr);
+        c->enc_trivial = false;
+        if (int32_t e = launch_encode(c, d_in, raw_stride, n_images, (uint64_t)desc->width * desc->height, desc->channels, hdr, d_out,
+                                      out_stride, cap, 0, nullptr, s, !in_place))
+            return e;
+        QB_CUDA(c->h_pin_out.reserve(sizeof(uint64_t) * (size_t)n_images));
+        QB_CUDA(cudaMemcpy2DAsync(c->h_pin_out.p, sizeof(uint64_t), c->results.p, sizeof(EncResult), sizeof(uint64_t), n_images,
+                                  cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        const auto* w = static_cast<const uint64_t*>(c->h_pin_out.p);
+        if (h_written) std::memcpy(h_written, w, sizeof(uint64_t) * (size_t)n_images);
+        if (staged_out) {  // only the bytes each image produced travel back
+            for (uint32_t k = 0; k < n_images; ++k)
+                if (w[k]) QB_CUDA(cudaMemcpyAsync(h_out + k * out_stride, d_out + k * out_stride, w[k], cudaMemcpyDeviceToHost, s));
+            QB_CUDA(cudaStreamSynchronize(s));
+        }
         return 0;
     }
 

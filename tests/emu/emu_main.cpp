@@ -123,7 +123,9 @@ extern "C"
         DecParams P{};
         P.qoi = qoi;
         if (n_images == 1) { P.offsets = nullptr; P.tile_first = nullptr; P.single[0] = offsets[0]; P.single[1] = offsets[1]; }
-        else { P.offsets = offsets; P.tile_first = tile_first.data(); }
+        std::vector<uint64_t> pairs;  // the kernels take {first byte, one past the last} per stream
+        for (uint32_t k = 0; k < n_images; ++k) pairs.push_back(offsets[k]), pairs.push_back(offsets[k + 1]);
+        if (n_images != 1) { P.offsets = pairs.data(); P.tile_first = tile_first.data(); }
         P.out = out; P.out_stride = out_stride; P.n_pixels = (uint64_t)w * h;
         P.width = w; P.height = h; P.target = target; P.flip = flip;
         P.n_images = n_images; P.n_tiles = (uint32_t)tiles; P.epoch = 3;

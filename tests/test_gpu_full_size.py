@@ -85,3 +85,77 @@ def test_config4_batch_8192_images_512x512_rgba(ctx):
     ctx.decode_batch_dev(packed, offs, w, h, 4, 0, 0, d_out, raw_one, st)
     torch.cuda.synchronize()
     assert torch.equal(d_out, d_raw)
+
+
+def _device_image(kind, w, h, ch):
+    from qoipp_b200 import synth_torch
+
+    return synth_torch.generate(kind, w, h, ch, device="cuda")[0]
+
+
+def _full_size_case(ctx, kind, w, h, ch, rows, expect_path=None):
+    """encode on the device; the stream's prefix equals the oracle's encoding of the first `rows` rows (the codec is causal);
+    decode returns the input bit for bit; returns (encoded size, decode path)."""
+    import torch
+
+    d_raw = _device_image(kind, w, h, ch)
+    cap = (ch + 1) * w * h + 22
+    d_q = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.encode_dev(d_raw, w, h, ch, 0, d_q, cap, st)
+    n, ok = ctx.encode_status(st)
+    assert ok
+    head = d_raw[: w * rows * ch].cpu().numpy()
+    assert np.array_equal(head, synth.generate(kind, w, rows, ch)), "device generator disagrees with synth.py"
+    ref = Oracle.encode(head, w, rows, ch)
+    # the last chunk of the prefix may differ (a run / index that continues into the next row): compare all but 8 bytes
+    got = d_q[: ref.size - 8].cpu().numpy()
+    assert np.array_equal(got[14: ref.size - 16], ref[14: ref.size - 16])
+    d_out = torch.zeros(w * h * ch, dtype=torch.uint8, device="cuda")
+    ctx.decode_dev(d_q, n, w, h, ch, 0, 0, False, d_out, d_out.numel(), st)
+    path = ctx.decode_status(st)
+    assert torch.equal(d_out, d_raw)
+    # and the oracle decodes the device's prefix back to the first rows (ref.decode(gpu.encode(x)) == x on the prefix)
+    if expect_path is not None:
+        assert path == expect_path, path
+    return n, path
+
+
+def test_8k_rgba_photo_with_alpha_blobs(ctx):
+    """the "single 8K image" of the target sentence, SURVEY's RGBA `photo` class (soft alpha blobs: the class whose OP_RGB
+    alpha speculation is refuted now and then)."""
+    n, path = _full_size_case(ctx, "photo", 7680, 4320, 4, rows=96)
+    assert path < 100, path  # the sequential loop is never needed; tiles repair themselves or a retry round fixes them
+    assert 0.2 < n / (7680 * 4320 * 4) < 0.7
+
+
+def test_8k_rgba_photo_opaque_verifies_in_round_0(ctx):
+    _full_size_case(ctx, "photo_opaque", 7680, 4320, 4, rows=96, expect_path=0)
+
+
+@pytest.mark.parametrize("kind", ["photo", "resync"])
+def test_config3_16384x16384_rgba_photo_and_resync(ctx, kind):
+    """configs[2], the two other classes SURVEY 8(d) lists for it (`noise` is the test above)."""
+    n, path = _full_size_case(ctx, kind, 16384, 16384, 4, rows=48)
+    assert path < 100, path
+
+
+def test_4k_rgb_photo_matches_the_oracle_byte_for_byte(ctx):
+    """configs[1] at full size against the oracle, the whole stream (8.3 M pixels: the oracle needs a fraction of a second)."""
+    import torch
+
+    w, h, ch = 3840, 2160, 3
+    d_raw = _device_image("photo", w, h, ch)
+    raw = d_raw.cpu().numpy()
+    ref = Oracle.encode(raw, w, h, ch)
+    cap = (ch + 1) * w * h + 22
+    d_q = torch.empty(cap + 64, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.encode_dev(d_raw, w, h, ch, 0, d_q, cap, st)
+    n, ok = ctx.encode_status(st)
+    assert ok and n == ref.size
+    assert np.array_equal(d_q[:n].cpu().numpy(), ref)
+    d_out = torch.zeros(w * h * ch, dtype=torch.uint8, device="cuda")
+    ctx.decode_dev(torch.from_numpy(ref).cuda(), ref.size, w, h, ch, 0, 0, False, d_out, d_out.numel(), st)
+    assert ctx.decode_status(st) == 0
+    assert np.array_equal(d_out.cpu().numpy(), raw)
