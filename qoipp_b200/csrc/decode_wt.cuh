@@ -40,6 +40,11 @@
 // (profiles/r02_experiments.md: 98 KB of SASS, hit rate 88 %, time proportional to the number of tiles whatever the
 // occupancy).  Helpers that are called once per tile, or are cold, are real calls instead of inlined copies.
 #define QB_NOINLINE __noinline__
+#if defined(QB_EMU) || defined(QB_NO_REPAIR_FENCE)
+#define QB_FENCE_SC() do { } while (0)
+#else
+#define QB_FENCE_SC() __threadfence()  // fence.sc.gpu
+#endif
 
 namespace qb
 {
@@ -439,15 +444,16 @@ namespace qb
     // changed.  Usually nothing read the one or two table slots in question and they are overwritten within a tile or two.
     // A changed pixel / alpha or slot word is not followed (everything behind the tile is flagged).  Cold.  One warp.
     __device__ QB_NOINLINE void wt_repair_scan(const DecParams& P, uint64_t* desc, unsigned t, unsigned ntiles, unsigned round, DecResult* res,
-                                               const Epochs& ep, const uint64_t (&old_word)[3])
+                                               const Epochs& ep, const uint64_t (&old_word)[3], unsigned dirty)
     {
         constexpr unsigned kScan = 16;  // tiles followed before giving up
         const unsigned     lane  = threadIdx.x & 31u;
         unsigned dlo = 0, dhi = 0, dprev = 0, hard = 0;
+        QB_FENCE_SC();  // this tile's republished words are ordered before the reads of the successors' need words (see wt_decode_tile)
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const unsigned wi = 1u + 32u * i + lane;
-            if (wi <= (unsigned)kDwState + 64u && ld_word(desc + wi) != old_word[i]) {
+            if (wi <= (unsigned)kDwState + 64u && (ld_word(desc + wi) != old_word[i] || ((dirty >> i) & 1u))) {
                 if (wi < (unsigned)kDwState) hard = 1;
                 else {
                     const unsigned e = wi - kDwState;
@@ -460,22 +466,33 @@ namespace qb
         dlo = __reduce_or_sync(kFull, dlo), dhi = __reduce_or_sync(kFull, dhi), dprev = __reduce_or_sync(kFull, dprev), hard = __reduce_or_sync(kFull, hard);
         if (!(dlo | dhi | dprev | hard)) return;  // the repaired tile says exactly what it said before
         unsigned u = t + 1u;
+#ifdef QB_REPAIR_ALWAYS_REDO
+        hard = 1;
+#endif
         if (!hard) {
             for (; u < ntiles && u <= t + kScan; ++u) {
                 const uint64_t* d_u = desc + (uint64_t)(u - t) * kDecDescWords;
-                const uint64_t  nl = word_payload(wait_word(d_u + kDwNeedLo, ep, u)), nh = word_payload(wait_word(d_u + kDwNeedHi, ep, u));
+                // never wait here: tile u may not even have been drawn yet, and the warp that would draw it may be this one's
+                // neighbour stuck in the same scan.  A tile that has not said what it reads is decoded again.
+                const uint64_t wl = ld_word(d_u + kDwNeedLo), wh = ld_word(d_u + kDwNeedHi);
+                if (!ep.valid(wl, u) || !ep.valid(wh, u)) break;
+                const uint64_t nl = word_payload(wl), nh = word_payload(wh);
                 if (((unsigned)nl & dlo) | ((unsigned)nh & dhi) | dprev) break;  // tile u read a changed entry (prev is always read)
                 // what tile u hands on: an entry is still changed if it is derived from a changed one
                 bool d[3];
+                bool missing = false;
 #pragma unroll
                 for (int hh = 0; hh < 3; ++hh) {
                     const unsigned e = lane + 32u * hh;
                     d[hh]            = false;
                     if (e <= 64u) {
-                        const unsigned ref = (unsigned)(word_payload(wait_word(d_u + kDwState + e, ep, u)) >> 32) & 0x7Fu;
+                        const uint64_t ws = ld_word(d_u + kDwState + e);
+                        if (!ep.valid(ws, u)) missing = true;
+                        const unsigned ref = (unsigned)(word_payload(ws) >> 32) & 0x7Fu;
                         d[hh] = ref < 32u ? (dlo >> ref) & 1u : (ref < 64u ? (dhi >> (ref - 32u)) & 1u : (ref == 64u ? dprev != 0 : false));
                     }
                 }
+                if (__ballot_sync(kFull, missing)) break;
                 dlo = __ballot_sync(kFull, d[0]), dhi = __ballot_sync(kFull, d[1]), dprev = __ballot_sync(kFull, d[2]) & 1u;
                 if (!(dlo | dhi | dprev)) return;  // every changed entry has been overwritten before anything read it
             }
@@ -590,8 +607,12 @@ namespace qb
         // repaired tile publishes the SAME words (the wrong alpha usually dies inside the tile: the next OP_RGBA resets it and
         // the table slots it touched are overwritten), nothing downstream changed and no retry round is needed.  One refuted
         // op in 18 000 tiles (RGBA photo with soft alpha blobs) used to cost a second decode of everything behind it.
-        constexpr unsigned kRepairPasses = 3;
-        uint64_t           old_word[3] = { 0, 0, 0 };  // this lane's share of words 1 .. 67 as first published
+#ifndef QB_REPAIR_PASSES
+#define QB_REPAIR_PASSES 3
+#endif
+        constexpr unsigned kRepairPasses = QB_REPAIR_PASSES;
+        uint64_t           old_word[3] = { 0, 0, 0 };  // this lane's share of words 1 .. 67 as published by the latest refuted pass
+        unsigned           dirty = 0;                  // bit i: word i of this lane differed between two refuted passes
         uint64_t           pix_base_f = 0;
         unsigned           n_pix_f = 0, fixn0 = sm.fixn0;
         bool               tail_fill_f = false, still_bad = false;
@@ -838,6 +859,11 @@ namespace qb
             st_word(desc + kDwNeedLo, pack_word(need_lo, ST_INCL, epoch));
             st_word(desc + kDwNeedHi, pack_word((uint64_t)1u << 32 | need_hi, ST_INCL, epoch));
         }
+        // The need words above and the reads of the predecessors' state words below are the two halves of a store-buffering
+        // pattern with a repairing predecessor (it republishes its words, then reads our need words, wt_repair_scan): without a
+        // sequentially consistent fence on both sides each could miss the other's store -- we would use a retracted word and
+        // the predecessor would not notice.
+        QB_FENCE_SC();
         if ((need_lo >> lane) & 1u) sm.rec[kIdExt + lane] = wt_resolve_entry(desc, t, lane, ep);
         if ((need_hi >> lane) & 1u) sm.rec[kIdExt + 32u + lane] = wt_resolve_entry(desc, t, lane + 32u, ep);
         if (lane == 0) sm.rec[kIdExt + 64u] = wt_resolve_entry(desc, t, 64u, ep);  // prev: nearly every tile reads it
@@ -945,11 +971,13 @@ namespace qb
         const unsigned nfail = sm.nfail;  // refuted OP_RGB ops (an OP_INDEX that read a never-written slot counts in `bad` only)
         if (nfail) wt_record_failures(P, sm, fix, B, cbeg + my_entry, opbase, nops);
         if (nfail == 0 || pass + 1u >= kRepairPasses) break;  // nothing learned, or not converging: the retry rounds take over
-        if (pass == 0) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (1u + 32u * i + lane <= (unsigned)kDwState + 64u) old_word[i] = ld_word(desc + 1 + 32 * i + lane);
-        }
+        for (int i = 0; i < 3; ++i)  // a successor may have read the words of ANY refuted pass: a word counts as changed if two passes disagree on it
+            if (1u + 32u * i + lane <= (unsigned)kDwState + 64u) {
+                const uint64_t now = ld_word(desc + 1 + 32 * i + lane);
+                if (pass > 0 && now != old_word[i]) dirty |= 1u << i;
+                old_word[i] = now;
+            }
         __syncwarp();
         fixn0 = sm.fixn;
         if (lane == 0) sm.fixn0 = fixn0, sm.nfail = 0;
@@ -958,7 +986,7 @@ namespace qb
         if (still_bad) {
             wt_flag_redo(P, round, res, t);  // the image is eligible for the next round, from this tile on
         } else if (pass) {  // repaired: did anything this tile told the others change, and did it matter?
-            wt_repair_scan(P, desc, t, ntiles, round, res, ep, old_word);
+            wt_repair_scan(P, desc, t, ntiles, round, res, ep, old_word, dirty);
         }
         QB_STAMP(desc, 75, 1, qb_t0);  // emit
 
