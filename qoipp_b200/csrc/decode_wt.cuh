@@ -198,7 +198,7 @@ namespace qb
         unsigned       rec[kWtNodes + 3];              // per node: value relative to its base (ops, E nodes, EXT entries)
         unsigned short base[kDecTB + 32];              // per op / E node: base node id
         alignas(4) unsigned char slot[kDecTB + 4];     // per op: slot | flags; an OP_RUN keeps its tag byte (0xC0 | run - 1)
-        unsigned short lastk[64];                      // last op per slot
+        unsigned       lastk[64];                      // 1 + last op per slot (0 = none), built with atomicMax
         unsigned       fixe[kFixWords];                // learned alphas: pos | alpha << 16
         unsigned       fails[kFixWords];               // OP_RGB ops refuted in this round: op ordinal | actual alpha << 16
         unsigned char  hE[32];                         // slot of the value entering each lane's chunk
@@ -783,39 +783,27 @@ namespace qb
         __syncwarp();
 
         QB_STAMP(desc, 76, 1, qb_t0);  // entry nodes + look-back 3
-        // ================= absolute slots, last op per slot (lane = op) =================
-        // lastk[s] = 1 + the last op of the tile whose value is stored in slot s (0 = none).  Steps run in stream order; inside a
-        // step several lanes may hold the same slot: all store, read back, and the lanes that lost to an EARLIER op store again
-        // (usually one retry).  __match_any_sync did this in one instruction but took 19 cycles per instruction of this loop.
-        for (unsigned kb = 0; kb < n_ops; kb += 32u) {
-            const unsigned k     = kb + lane;
-            unsigned       s     = 64u;
-            if (k < n_ops) {
-                const unsigned s8 = sm.slot[k], b = sm.base[k];
-                if (s8 < 0xC0u) {  // an OP_RUN repeats its predecessor: never the only writer of a slot
-                    s = s8 & 63u;
-                    if (b >= kIdE && b < kIdExt) {  // before the lane's first root: the walk knew the slot relative to the lane's entry
-                        s = (s + sm.hE[b - kIdE]) & 63u;
-                        if (any_idx) sm.slot[k] = (unsigned char)(s | (s8 & 0xC0u));  // the searches below compare absolute slots
-                    } else if (b == kIdAbsA) {  // a literal with the tile's entry alpha
-                        s = (s + 11u * ain) & 63u;
-                        if (any_idx) sm.slot[k] = (unsigned char)(s | (s8 & 0xC0u));
-                    }
+        // ================= absolute slots, last op per slot =================
+        // lastk[s] = 1 + the last op of the tile whose value is stored in slot s (0 = none).
+        // Lane-serial: every lane runs over its own ops (the ones it recorded in the walk), so the lane's entry slot is a
+        // register and "before the lane's first root" needs no search; the last writer of a slot is an atomicMax in shared
+        // memory.  (Lane = op, this phase cost 32 ops per ~30 instructions with a store / read-back / retry loop for equal slots;
+        // here it is 32 ops per ~10.)
+        {
+            const unsigned hEl = sm.hE[lane], ownE = kIdE + lane, a11 = 11u * ain;
+            for (unsigned j = 0, k = opbase; j < nops; ++j, ++k) {
+                const unsigned s8 = sm.slot[k];
+                if (s8 >= 0xC0u) continue;  // an OP_RUN repeats its predecessor: never the only writer of a slot
+                const unsigned b = sm.base[k];
+                unsigned       s = s8 & 63u;
+                if (b == ownE || b == kIdAbsA) {  // the walk knew the slot relative to the lane's entry / to the tile's entry alpha
+                    s = (s + (b == ownE ? hEl : a11)) & 63u;
+                    if (any_idx) sm.slot[k] = (unsigned char)(s | (s8 & 0xC0u));  // the searches below compare absolute slots
                 }
+                atomicMax(&sm.lastk[s], k + 1u);
             }
-#ifdef QB_WT_MATCH
-            const unsigned m = __match_any_sync(kFull, s < 64u ? s : 64u + lane);
-            if (s < 64u && (m & lanemask_gt(lane)) == 0) sm.lastk[s] = (unsigned short)(k + 1u);
-            __syncwarp();
-#else
-            bool again = s < 64u;
-            do {
-                if (again) sm.lastk[s] = (unsigned short)(k + 1u);
-                __syncwarp();
-                again = s < 64u && sm.lastk[s] < k + 1u;
-            } while (__ballot_sync(kFull, again));
-#endif
         }
+        __syncwarp();
         QB_STAMP(desc, 74, 0, qb_t0);  // slots + last writers
 
         // ================= OP_INDEX ops: writers (backward search over slot[]) and pointer jumping =================
@@ -868,7 +856,6 @@ namespace qb
         if ((need_hi >> lane) & 1u) sm.rec[kIdExt + 32u + lane] = wt_resolve_entry(desc, t, lane + 32u, ep);
         if (lane == 0) sm.rec[kIdExt + 64u] = wt_resolve_entry(desc, t, 64u, ep);  // prev: nearly every tile reads it
         __syncwarp();
-        const unsigned prev_in = sm.rec[kIdExt + 64u];
         // now-known entries become inclusive words, so later tiles stop here
 #pragma unroll
         for (int hh = 0; hh < 3; ++hh) {
@@ -895,6 +882,9 @@ namespace qb
         QB_STAMP(desc, 75, 0, qb_t0);  // state look-back
 
         // ================= emit: values, verification, pixels (lane = op) =================
+        // (A lane-serial emit -- every lane running over its own ops with the previous value and the pixel offset in registers,
+        // ~20 instructions per 32 ops instead of ~80 -- was measured and lost: its 32 stores per instruction go to 32 different
+        // places, ~20-30 cycles of LSU time each; 4K RGB 178 -> 233 us, 8K RGBA 694 -> 786 us.  profiles/r02_experiments.md)
         bool           bad    = false;
         const unsigned live_n = pix_base < N ? (unsigned)(N - pix_base < 0xFFFFFFFFull ? N - pix_base : 0xFFFFFFFFull) : 0u;  // pixels of this tile inside the image
         const unsigned tgt    = P.target;
@@ -902,7 +892,7 @@ namespace qb
         // FAST: rows top-down and (four-byte pixels) a word-aligned image; else the general store_pixel
         const bool fast = !P.flip && (tgt == 3u || (reinterpret_cast<uintptr_t>(out) & 3u) == 0);
         {
-            unsigned       carry   = prev_in;  // value of the op before this step's first one
+            unsigned       carry   = sm.rec[kIdExt + 64u];  // value of the op before this step's first one (prev entering the tile)
             unsigned       xcarry  = 0;        // extra OP_RUN pixels before this step
             const unsigned* recp   = sm.rec + lane;
             const unsigned short* basep = sm.base + lane;
