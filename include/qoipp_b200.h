@@ -44,6 +44,20 @@ typedef struct qoipp_b200_state {
     uint8_t seen[64][4];
 } qoipp_b200_state;
 
+/* The same state resident in device memory (the resumable *_dev entry points): pixels packed r | g<<8 | b<<16 | a<<24,
+ * `run` = pending run pixels (decoder) / current run length (encoder). */
+typedef struct qoipp_b200_dev_state {
+    uint32_t prev;
+    uint32_t run;
+    uint32_t seen[64];
+} qoipp_b200_dev_state;
+
+/* StreamResult{processed, written} (include/qoipp/common.hpp:148-152), both in bytes, written by the device */
+typedef struct qoipp_b200_stream_result {
+    uint64_t processed;
+    uint64_t written;
+} qoipp_b200_stream_result;
+
 /* Opaque per-thread context: device workspace for the tile carries, pinned staging, result slots.
  * One context serves one host thread / stream at a time; create as many as there are driving threads. */
 typedef struct qoipp_b200_ctx qoipp_b200_ctx;
@@ -88,6 +102,10 @@ int32_t qoipp_b200_encode_batch_host(qoipp_b200_ctx* ctx, const uint8_t* h_raw, 
 
 /* ---- resumable encode: replaces StreamEncoder::encode (source/stream.cpp:138-239).  `state` is carried by the
  * caller between calls; in_size is truncated to whole pixels (stream.cpp:59). */
+/* device buffers; asynchronous on `stream`: *d_state is read and replaced, *d_result is written; no host synchronisation */
+int32_t qoipp_b200_stream_encode_dev(qoipp_b200_ctx* ctx, uint8_t channels, qoipp_b200_dev_state* d_state, const uint8_t* d_in,
+                                     uint64_t in_size, uint8_t* d_out, uint64_t out_cap, qoipp_b200_stream_result* d_result,
+                                     void* stream);
 int32_t qoipp_b200_stream_encode_host(qoipp_b200_ctx* ctx, qoipp_b200_state* state, const uint8_t* h_in, uint64_t in_size,
                                       uint8_t* h_out, uint64_t out_cap, uint64_t* processed, uint64_t* written);
 
@@ -124,7 +142,14 @@ int32_t qoipp_b200_decode_batch_host(qoipp_b200_ctx* ctx, const uint8_t* h_qoi, 
                                      uint32_t n_images, const qoipp_b200_desc* desc, uint8_t target_channels, uint8_t* h_out,
                                      uint64_t out_stride);
 
-/* ---- resumable decode: replaces StreamDecoder::decode / drain_run (source/stream.cpp:312-447). */
+/* ---- resumable decode: replaces StreamDecoder::decode / drain_run (source/stream.cpp:312-447).
+ * Inputs of a few KB and more are decoded by the same parallel tile kernel as a whole image, with `state` as the carry-in
+ * and the carry-out taken behind the last consumed op; an incomplete op at the end of the input is not consumed
+ * (stream.cpp:341-392).  Shorter inputs, and calls whose content refutes the kernel's speculation, take a sequential loop. */
+/* device buffers; asynchronous on `stream`: *d_state is read and replaced, *d_result is written; no host synchronisation */
+int32_t qoipp_b200_stream_decode_dev(qoipp_b200_ctx* ctx, uint8_t channels, qoipp_b200_dev_state* d_state, const uint8_t* d_in,
+                                     uint64_t in_size, uint8_t* d_out, uint64_t out_cap, qoipp_b200_stream_result* d_result,
+                                     void* stream);
 int32_t qoipp_b200_stream_decode_host(qoipp_b200_ctx* ctx, qoipp_b200_state* state, const uint8_t* h_in, uint64_t in_size,
                                       uint8_t* h_out, uint64_t out_cap, uint64_t* processed, uint64_t* written);
 

@@ -57,12 +57,14 @@ def _load():
         "qoipp_b200_encode_batch_host": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, dp, vp, C.c_uint64, C.c_uint64, u64p]),
         "qoipp_b200_decode_batch_strided_dev": (C.c_int32, [vp, vp, C.c_uint64, u64p, C.c_uint32, dp, C.c_uint8, vp, C.c_uint64, vp]),
         "qoipp_b200_decode_batch_host": (C.c_int32, [vp, vp, C.c_uint64, u64p, C.c_uint32, dp, C.c_uint8, vp, C.c_uint64]),
+        "qoipp_b200_stream_encode_dev": (C.c_int32, [vp, C.c_uint8, vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
         "qoipp_b200_stream_encode_host": (C.c_int32, [vp, C.POINTER(State), vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]),
         "qoipp_b200_decode_dev": (C.c_int32, [vp, vp, C.c_uint64, dp, C.c_uint8, C.c_int32, vp, C.c_uint64, vp]),
         "qoipp_b200_decode_status": (C.c_int32, [vp, vp, i32p]),
         "qoipp_b200_decode_status_batch": (C.c_int32, [vp, vp, i32p, C.c_uint32]),
         "qoipp_b200_decode_host": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint8, C.c_int32, vp, C.c_uint64, dp]),
         "qoipp_b200_decode_batch_dev": (C.c_int32, [vp, vp, u64p, C.c_uint32, dp, C.c_uint8, vp, C.c_uint64, vp]),
+        "qoipp_b200_stream_decode_dev": (C.c_int32, [vp, C.c_uint8, vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp]),
         "qoipp_b200_stream_decode_host": (C.c_int32, [vp, C.POINTER(State), vp, C.c_uint64, vp, C.c_uint64, u64p, u64p]),
     }
     for name in declared_symbols():

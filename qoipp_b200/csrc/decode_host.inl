@@ -224,6 +224,55 @@ extern "C"
         return 0;
     }
 
+    // ---- resumable decode on device buffers: everything is enqueued on `stream`, nothing waits for the device
+    int32_t qoipp_b200_stream_decode_dev(qoipp_b200_ctx* c, uint8_t channels, qoipp_b200_dev_state* d_state, const uint8_t* d_in,
+                                         uint64_t in_size, uint8_t* d_out, uint64_t out_cap, qoipp_b200_stream_result* d_result, void* stream)
+    {
+        if (channels != 3 && channels != 4) return H::NotInitialized;  // error order of StreamDecoder::decode, stream.cpp:314-320
+        if (out_cap == 0) return H::Empty;
+        if (out_cap < channels) return H::TooShort;
+        Guard g(c->device);
+        auto  s = static_cast<cudaStream_t>(stream);
+        QB_CUDA(set_attrs(c));
+        const uint64_t room = out_cap / channels;  // pixels
+        if (room >= kPixSat) return H::TooBig;
+        const uint64_t tiles = (in_size + kDecTB - 1) / kDecTB;
+        if (tiles >= (1ull << 31)) return H::TooBig;
+        const size_t res_bytes = kCtrlBytes + sizeof(DecResult);
+        QB_CUDA(c->results.reserve(res_bytes, s));
+        QB_CUDA(cudaMemsetAsync(c->results.p, 0, res_bytes, s));
+        auto* d_res = reinterpret_cast<DecResult*>(static_cast<uint8_t*>(c->results.p) + kCtrlBytes);
+        SerialParams S{};
+        S.d.qoi = d_in, S.d.single[0] = 0, S.d.single[1] = in_size;
+        S.d.out = d_out, S.d.out_stride = room * channels;  // mode 1: capacity in bytes
+        S.d.target = channels, S.d.flip = 0, S.d.n_images = 1, S.d.n_pixels = room;
+        S.d.results = d_res;
+        S.mode = 1, S.init = reinterpret_cast<const DecState*>(d_state), S.in_size = in_size, S.only_if_bad = 0;
+        // The parallel kernel needs a few tiles to be worth its launch; a short buffer (and a call that has nothing to read) is
+        // decoded by the sequential loop alone.
+        if (in_size >= c->stream_parallel_min && tiles > 0) {
+            DecParams& P = S.d;
+            QB_CUDA(c->fix.reserve((size_t)tiles * kFixWords * sizeof(uint32_t), s, true));
+            QB_CUDA(c->next_epoch(tiles * kDecDescWords * sizeof(uint64_t), s, kDecRounds + 1));
+            P.offsets = nullptr, P.tile_first = nullptr;
+            P.n_tiles = (uint32_t)tiles, P.epoch = c->epoch, P.round = 0;
+            P.control = static_cast<DecControl*>(c->results.p);
+            P.desc    = static_cast<uint64_t*>(c->carry.p);
+            P.fix     = static_cast<uint32_t*>(c->fix.p);
+            P.init    = S.init;
+            const unsigned want   = ((unsigned)tiles + kWtWarps - 1) / kWtWarps;
+            const unsigned n_ctas = std::max(1u, std::min<unsigned>(want, (unsigned)c->dec_coresident));
+            decode_wt_stream_kernel<<<n_ctas, kWtThreads, kWtSmemBytes, s>>>(P);
+            QB_CUDA(cudaGetLastError());
+            S.only_if_bad = 1;  // the sequential loop behind it runs only if a speculation was refuted
+        }
+        decode_serial_kernel<<<1, 32, sizeof(SerialSmem), s>>>(S);
+        QB_CUDA(cudaGetLastError());
+        stream_decode_epilogue_kernel<<<1, 64, 0, s>>>(d_res, reinterpret_cast<StreamOut*>(d_result), reinterpret_cast<DecState*>(d_state));
+        QB_CUDA(cudaGetLastError());
+        return 0;
+    }
+
     int32_t qoipp_b200_stream_decode_host(qoipp_b200_ctx* c, qoipp_b200_state* st, const uint8_t* h_in, uint64_t in_size,
                                           uint8_t* h_out, uint64_t out_cap, uint64_t* processed, uint64_t* written)
     {
@@ -240,32 +289,30 @@ extern "C"
         cudaStream_t s  = c->own_stream;
         QB_CUDA(c->stage_in.reserve(in_size + 64, s));
         QB_CUDA(c->stage_out.reserve(cap + 64, s));
-        QB_CUDA(c->state.reserve(sizeof(DecState), s));
-        QB_CUDA(c->results.reserve(kCtrlBytes + sizeof(DecResult), s));
-        auto*        hs = reinterpret_cast<DecState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
+        QB_CUDA(c->state.reserve(sizeof(DecState) + sizeof(StreamOut), s));
+        auto* d_state = static_cast<DecState*>(c->state.p);
+        auto* d_sres  = reinterpret_cast<StreamOut*>(d_state + 1);
+        // pinned block: [0] carry-in, [1] carry-out + result
+        auto* hs = reinterpret_cast<DecState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
         hs->prev = pack_px(st->prev), hs->run = st->run;
         for (int i = 0; i < 64; ++i) hs->table[i] = pack_px(st->seen[i]);
-        QB_CUDA(cudaMemcpyAsync(c->state.p, hs, sizeof(DecState), cudaMemcpyHostToDevice, s));
-        if (in_size) QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_in, in_size, cudaMemcpyHostToDevice, s));
-        SerialParams S{};
-        S.d.qoi = static_cast<uint8_t*>(c->stage_in.p), S.d.single[0] = 0, S.d.single[1] = in_size;
-        S.d.out = static_cast<uint8_t*>(c->stage_out.p), S.d.out_stride = cap;  // mode 1: capacity in bytes
-        S.d.target = ch, S.d.flip = 0, S.d.n_images = 1;
-        S.d.results = reinterpret_cast<DecResult*>(static_cast<uint8_t*>(c->results.p) + kCtrlBytes);
-        S.mode = 1, S.init = static_cast<DecState*>(c->state.p), S.in_size = in_size;
-        decode_serial_kernel<<<1, 32, sizeof(SerialSmem), s>>>(S);
-        QB_CUDA(cudaGetLastError());
-        auto* hr = static_cast<DecResult*>(c->h_result.p);
-        QB_CUDA(cudaMemcpyAsync(hr, static_cast<uint8_t*>(c->results.p) + kCtrlBytes, sizeof(DecResult), cudaMemcpyDeviceToHost, s));
-        QB_CUDA(cudaStreamSynchronize(s));
-        if (hr->written) {
-            QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, hr->written, cudaMemcpyDeviceToHost, s));
-            QB_CUDA(cudaStreamSynchronize(s));
+        QB_CUDA(cudaMemcpyAsync(d_state, hs, sizeof(DecState), cudaMemcpyHostToDevice, s));
+        if (in_size) {
+            if (const uint8_t* m = mapped_host(h_in); m && in_size < (1u << 20)) QB_CUDA(cudaMemcpyAsync(c->stage_in.p, m, in_size, cudaMemcpyDefault, s));
+            else QB_CUDA(pageable_to_device(c, c->stage_in.p, h_in, in_size, s));
         }
-        *processed = hr->processed, *written = hr->written;
-        unpack_px(hr->state.prev, st->prev);
-        st->run = (uint8_t)hr->state.run;
-        for (int i = 0; i < 64; ++i) unpack_px(hr->state.table[i], st->seen[i]);
+        if (int32_t e = qoipp_b200_stream_decode_dev(c, (uint8_t)ch, reinterpret_cast<qoipp_b200_dev_state*>(d_state), static_cast<uint8_t*>(c->stage_in.p), in_size,
+                                                     static_cast<uint8_t*>(c->stage_out.p), cap, reinterpret_cast<qoipp_b200_stream_result*>(d_sres), s))
+            return e;
+        auto* hr = reinterpret_cast<DecState*>(static_cast<uint8_t*>(c->h_result.p) + 2048);
+        QB_CUDA(cudaMemcpyAsync(hr, d_state, sizeof(DecState) + sizeof(StreamOut), cudaMemcpyDeviceToHost, s));
+        QB_CUDA(cudaStreamSynchronize(s));
+        const auto* ho = reinterpret_cast<const StreamOut*>(hr + 1);
+        if (ho->written) QB_CUDA(device_to_pageable(c, h_out, c->stage_out.p, ho->written, s));
+        *processed = ho->processed, *written = ho->written;
+        unpack_px(hr->prev, st->prev);
+        st->run = (uint8_t)hr->run;
+        for (int i = 0; i < 64; ++i) unpack_px(hr->table[i], st->seen[i]);
         return 0;
     }
 }

@@ -87,6 +87,7 @@ namespace qb
         DecControl*     control;
         uint64_t*       desc;
         uint32_t*       fix;  // [n_tiles][kFixWords]: alpha learned at OP_RGB ops by earlier rounds
+        const DecState* init;  // resumable decode (wt_decode_tile<true>): the state the chunk stream is entered with; null otherwise
     };
 
 #ifndef QB_WT_CHUNK
@@ -275,12 +276,13 @@ namespace qb
             acc = pixa_comb(acc, wt_fold32(min(n - o, 32u), [&](unsigned i) { return wt_wait_pixa(d_t, t, first + (o + i) * step, which, ep); }));
         return acc;
     }
-    __device__ QB_NOINLINE PixA wt_gather_pixa(const uint64_t* d_t, unsigned t, const Epochs& ep)
+    __device__ QB_NOINLINE PixA wt_gather_pixa(const uint64_t* d_t, unsigned t, const Epochs& ep, const DecState* init = nullptr)
     {
         // (A variant that issued the tile-word and group-word loads of a lane together, four in flight, decoded wrongly on
         // the B200 although it is equivalent on paper and passes in the emulator -- profiles/r02_experiments.md; the folds
         // stay one after the other.)
         PixA           acc{ 0u, 0u, 0x1FFu };  // before the stream: no pixels, alpha 255
+        if (init) acc = PixA{ init->run, 0u, 0x100u | (init->prev >> 24) };  // resumable decode: the pending run comes first (stream.cpp:335-339)
         const unsigned s = t / kSup, g = t / kGrp, r = t % kGrp;
         for (unsigned j = 0; j < s; j += 64u)  // super-groups before mine
             acc = pixa_comb(acc, wt_fold_words(d_t, t, j * kSup + kSup - 1u, min(64u, s - j), kSup, kDwSup, ep));
@@ -303,10 +305,11 @@ namespace qb
 
     // incoming value of state entry `e` (0..63 table slot, 64 prev) of tile `t`: follow the chain of transfer words
     // through the predecessors until a constant (inclusive word) or the start of the stream.  `d_t` = descriptor of tile t.
-    __device__ QB_NOINLINE unsigned wt_resolve_entry(const uint64_t* d_t, unsigned t, unsigned e, const Epochs& ep)
+    __device__ QB_NOINLINE unsigned wt_resolve_entry(const uint64_t* d_t, unsigned t, unsigned e, const Epochs& ep, const DecState* init = nullptr)
     {
         unsigned acc = 0;
         for (int p = (int)t - 1;; --p) {
+            if (p < 0 && init) return add4(e == 64u ? init->prev : init->table[e], acc);  // stream.hpp:239-243
             if (p < 0) return add4((e == 64u || e == 53u) ? kStartPixel : 0u, acc);  // simple.cpp:103-108
             const uint64_t wd = wait_word(d_t - (int64_t)(t - (unsigned)p) * kDecDescWords + kDwState + (int)e, ep, (unsigned)p);
             const uint64_t pl = word_payload(wd);
@@ -501,13 +504,21 @@ namespace qb
         if (u < ntiles) wt_flag_redo(P, round, res, u);
     }
 
-    // one tile (global ticket `gticket`) of round `round`; one warp
+    // one tile (global ticket `gticket`) of round `round`; one warp.
+    // kStream = the resumable decode (StreamDecoder::decode, stream.cpp:312-424): the buffer has no header, the state the
+    // stream is entered with is P.init instead of the constants, a pending run comes first, P.n_pixels is the room in the
+    // output, an op that the input does not hold completely is not consumed (stream.cpp:341-392), and the tile that holds
+    // the last consumed op ("final tile") reports bytes consumed, bytes written and the state to carry on with.  Tiles behind
+    // it do nothing.  A refuted speculation is not retried here: the call falls back to the sequential loop.
+    template <bool kStream = false>
     __device__ __forceinline__ void wt_decode_tile(const DecParams& P, WtSmem& sm, const uint2* lut, unsigned round, unsigned gticket, unsigned img,
                                                    unsigned t, unsigned ntiles, const uint8_t* stream, uint64_t size, unsigned fresh_from)
     {
         const unsigned lane = threadIdx.x & 31u;
         [[maybe_unused]] const long long qb_t0 = QB_T0();
-        const uint64_t body_len = size - kHeader;  // every byte after the header is chunk data (simple.cpp:110-113)
+        constexpr unsigned kSkip   = kStream ? 0u : kHeader;
+        const DecState*    init    = kStream ? P.init : nullptr;
+        const uint64_t body_len = size - kSkip;  // every byte after the header is chunk data (simple.cpp:110-113)
         const uint64_t tile_b0  = (uint64_t)t * kDecTB;
         const unsigned limit    = (unsigned)(body_len - tile_b0 < (uint64_t)kDecTB ? body_len - tile_b0 : (uint64_t)kDecTB);
         uint64_t*      desc     = P.desc + (uint64_t)gticket * kDecDescWords;
@@ -531,7 +542,7 @@ namespace qb
         }
 
         // ---- stage the tile: 16-byte aligned vectors land at the same misalignment in shared memory
-        const uint8_t* src   = stream + kHeader + tile_b0;
+        const uint8_t* src   = stream + kSkip + tile_b0;
         const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
         {
             const uint64_t avail = body_len - tile_b0;  // bytes of the stream from the tile start
@@ -616,6 +627,9 @@ namespace qb
         uint64_t           pix_base_f = 0;
         unsigned           n_pix_f = 0, fixn0 = sm.fixn0;
         bool               tail_fill_f = false, still_bad = false;
+        [[maybe_unused]] unsigned fin_val[3] = { 0, 0, 0 }, fin_rem = 0;
+        [[maybe_unused]] uint64_t fin_made = 0, fin_used = 0;
+        [[maybe_unused]] bool     fin_final = false;
         unsigned           pass = 0;
         for (;; ++pass) {
         // ================= counts of the true path, look-back 2: pixels and inherited alpha =================
@@ -649,7 +663,7 @@ namespace qb
                 }
             }
         }
-        unsigned opbase, n_ops, n_pix, alpha_lane;  // alpha_lane: 0x100 | alpha when an earlier lane of this tile sets it, else 0
+        unsigned opbase, pix_lane, n_ops, n_pix, alpha_lane;  // alpha_lane: 0x100 | alpha when an earlier lane of this tile sets it, else 0
         {
             const unsigned mine = npx_lane | nops << 16;
             unsigned       inc  = mine, ai = a_sum;
@@ -664,7 +678,7 @@ namespace qb
             const unsigned tot = __shfl_sync(kFull, inc, 31), atot = __shfl_sync(kFull, ai, 31);
             unsigned       aex = __shfl_up_sync(kFull, ai, 1);
             if (lane == 0) aex = 0;
-            opbase = (inc - mine) >> 16;
+            opbase = (inc - mine) >> 16, pix_lane = (inc - mine) & 0xFFFFu;
             n_ops = tot >> 16, n_pix = tot & 0xFFFFu;
             const PixA agg{ n_pix, 0u, atot };
             if (lane == 0) st_word(desc + kDwPixA, pack_word(pixa_pack(agg), ST_INCL, epoch));
@@ -678,7 +692,7 @@ namespace qb
         // length and the flags; a literal overrides by selects; only OP_INDEX and learned alphas branch.  r and b accumulate in
         // two 16-bit lanes of one register (carries stay inside a lane for the <= 28 ops of a chunk), g in another.
         unsigned idxm = 0;  // OP_INDEX ops of this lane (bit = op number within the lane)
-        unsigned exit_bid, exit_h, exit_rec;
+        unsigned exit_bid, exit_h, exit_rec, exit_p;
         {
             const unsigned* S32 = reinterpret_cast<const unsigned*>(sm.bytes);
             unsigned        p = cbeg + my_entry, k = opbase, j = 0;
@@ -709,7 +723,7 @@ namespace qb
                 sm.slot[k] = (unsigned char)(fl == (kSlRgb | kSlIdx) ? tag : ((h & 63u) | fl));  // an OP_RUN keeps its tag
                 ++k, ++j, p += (L.y >> 14) & 7u;
             }
-            exit_bid = bid, exit_h = h & 63u, exit_rec = recv;
+            exit_bid = bid, exit_h = h & 63u, exit_rec = recv, exit_p = p;
         }
         QB_STAMP(desc, 77, 1, qb_t0);  // walk loop
         sm.lastk[lane] = 0, sm.lastk[lane + 32] = 0;
@@ -717,10 +731,51 @@ namespace qb
         // ---- look-back 2 (no chain, see wt_gather_pixa): pixels before the tile and the alpha entering it.  Taken AFTER the
         // walk: by now the tiles before this one have long published their counts (before the walk, every tile waited here for
         // the slowest of all its predecessors to finish parsing: a third of the tile time).
-        const PixA     pin      = wt_gather_pixa(desc, t, ep);
+        const PixA     pin      = wt_gather_pixa(desc, t, ep, init);
         const uint64_t pix_base = (uint64_t)pin.hi << 32 | pin.lo;
         const unsigned ain      = pin.a & 255u;
         if (lane == 0) sm.rec[kIdAbsA] = ain << 24;
+        unsigned n_keep = n_ops;  // ops of this tile that are executed (all of them, except in the final tile of a resumable decode)
+        [[maybe_unused]] bool     final_tile = false;
+        [[maybe_unused]] unsigned run_rem = 0, final_endp = 0;
+        [[maybe_unused]] uint64_t final_made = 0, final_used = 0;  // pixels in the output / input bytes consumed when this is the final tile
+        if constexpr (kStream) {
+            (void)pix_lane, (void)exit_p;
+            if (t == 0) {  // the pending run comes first (stream.cpp:335-339)
+                const uint64_t pre = (uint64_t)init->run < N ? (uint64_t)init->run : N;
+                for (uint64_t q = lane; q < pre; q += 32u) store_pixel(out, q, init->prev, P);
+            }
+            // only the last op of the whole input can be incomplete: it is left for the next call
+            const bool     incomplete = __ballot_sync(kFull, t == ntiles - 1u && nops != 0 && exit_p > limit) != 0;
+            const unsigned keep_ops = n_ops - (incomplete ? 1u : 0u), keep_pix = n_pix - (incomplete ? 1u : 0u);
+            if (pix_base >= N) {
+                if (t > 0) return;  // the output was full before this tile: nothing of it is consumed
+                final_tile = true, n_keep = 0, run_rem = (unsigned)(pix_base - N), final_made = N, final_used = 0;  // not even the pending run fits
+            } else if (pix_base + keep_pix >= N || t == ntiles - 1u) {
+                final_tile = true;
+                // the op that holds the last pixel that fits (the output is the limit), else the last complete op (the input is)
+                const bool     by_room = pix_base + keep_pix >= N;
+                const unsigned target  = by_room ? (unsigned)(N - 1u - pix_base) : 0u;
+                unsigned       kcut = 0, rem = 0, endp = 0;
+                bool           hit = false;
+                {
+                    unsigned p = cbeg + my_entry, po = pix_lane;
+                    for (unsigned j = 0, k = opbase; j < nops && k < keep_ops; ++j, ++k) {
+                        const unsigned tag = B[p], len = op_length(tag), ext = (tag >= kOpRun && tag < kOpRgb) ? (tag & 63u) : 0u;
+                        if (by_room ? (po <= target && target <= po + ext) : (k + 1u == keep_ops)) hit = true, kcut = k, rem = by_room ? po + ext - target : 0u, endp = p + len;
+                        po += 1u + ext, p += len;
+                    }
+                }
+                const unsigned who = __ballot_sync(kFull, hit);
+                if (who) {
+                    const int src = __ffs((int)who) - 1;
+                    n_keep = __shfl_sync(kFull, kcut, src) + 1u, run_rem = __shfl_sync(kFull, rem, src), final_endp = __shfl_sync(kFull, endp, src);
+                } else {
+                    n_keep = 0, final_endp = tile_entry;  // no complete op starts in this tile
+                }
+                final_made = by_room ? N : pix_base + keep_pix, final_used = tile_b0 + final_endp;
+            }
+        }
         QB_STAMP(desc, 76, 0, qb_t0);  // walk + gather
         if (exit_bid == kIdAbsA) exit_h = (exit_h + 11u * ain) & 63u;  // util.hpp:347-351: the alpha's share of the slot
         // `prev` leaving the tile is known already when the last op follows a literal: inclusive at once, the next tile waits less
@@ -728,7 +783,7 @@ namespace qb
         {
             const unsigned last_lane = 31u - (unsigned)__clz((int)(__ballot_sync(kFull, nops != 0) | 1u));
             const unsigned lb = __shfl_sync(kFull, exit_bid, (int)last_lane), lr = __shfl_sync(kFull, exit_rec, (int)last_lane);
-            prev_done = n_ops != 0 && lb == kIdAbs;
+            prev_done = n_ops != 0 && lb == kIdAbs && n_keep == n_ops;
             if (prev_done && lane == 0) st_word(desc + kDwState + 64, pack_word((uint64_t)65u << 32 | lr, ST_INCL, epoch));
         }
         // entry nodes: the value entering lane l's chunk = the value of the op before its first one
@@ -765,7 +820,7 @@ namespace qb
             if (lane == 0) ex = 0;
             if (lane == 0 && t > 0) st_word(desc + kDwSlot, pack_word(tot, (tot & 64u) ? ST_INCL : ST_AGG, epoch));
             const unsigned in = warp_lookback_lazy<unsigned>(
-                t, 64u | 53u, 0u,  // {0,0,0,255}: slot 53 (simple.cpp:108)
+                t, kStream ? 64u | slot_of(init->prev) : 64u | 53u, 0u,  // {0,0,0,255}: slot 53 (simple.cpp:108); resumable: the carried pixel
                 [&](unsigned p, unsigned& st) {
                     if (p < ep.fresh_from) {  // a tile finished by an earlier round: take the slot of its actual last pixel
                         const uint64_t wd = ld_word(word_of(p, kDwState + 64));
@@ -791,7 +846,7 @@ namespace qb
         // here it is 32 ops per ~10.)
         {
             const unsigned hEl = sm.hE[lane], ownE = kIdE + lane, a11 = 11u * ain;
-            for (unsigned j = 0, k = opbase; j < nops; ++j, ++k) {
+            for (unsigned j = 0, k = opbase; j < nops && k < n_keep; ++j, ++k) {
                 const unsigned s8 = sm.slot[k];
                 if (s8 >= 0xC0u) continue;  // an OP_RUN repeats its predecessor: never the only writer of a slot
                 const unsigned b = sm.base[k];
@@ -814,14 +869,14 @@ namespace qb
         // ================= the tile's transfer function: entries it can state now =================
         // entry e = lane, lane + 32 (table slots) and, in lane 0, 64 (prev)
         unsigned pub_ref[3], pub_add[3];  // ref: 0..64 = incoming entry, 65 = constant (published inclusive already)
-        const bool tail_fill = t == ntiles - 1 && pix_base + n_pix < N;  // the stream ends before the image does
+        const bool tail_fill = !kStream && t == ntiles - 1 && pix_base + n_pix < N;  // the stream ends before the image does
 #pragma unroll
         for (int hh = 0; hh < 3; ++hh) {
             const unsigned e = lane + 32u * hh;
             pub_ref[hh] = 66u, pub_add[hh] = 0;
             if (e > 64u) continue;
-            const unsigned k = e < 64u ? (unsigned)sm.lastk[e] - 1u : n_ops - 1u;  // 0xFFFFFFFF = none
-            const bool     none = e < 64u ? sm.lastk[e] == 0 : n_ops == 0;
+            const unsigned k = e < 64u ? (unsigned)sm.lastk[e] - 1u : n_keep - 1u;  // 0xFFFFFFFF = none
+            const bool     none = e < 64u ? sm.lastk[e] == 0 : n_keep == 0;
             unsigned       ref = e, add = 0;
             if (!none) {
                 unsigned b = sm.base[k];
@@ -839,6 +894,7 @@ namespace qb
             }
         }
         if (tail_fill) need_lo |= 1u;  // the zero padding decodes as OP_INDEX 0
+        if (kStream && final_tile) need_lo = need_hi = 0xFFFFFFFFu;  // the state to carry on with is all 65 entries
         QB_STAMP(desc, 77, 0, qb_t0);  // transfer function
 
         // ================= look-back 4: the entries of the incoming state that are read =================
@@ -852,9 +908,9 @@ namespace qb
         // sequentially consistent fence on both sides each could miss the other's store -- we would use a retracted word and
         // the predecessor would not notice.
         QB_FENCE_SC();
-        if ((need_lo >> lane) & 1u) sm.rec[kIdExt + lane] = wt_resolve_entry(desc, t, lane, ep);
-        if ((need_hi >> lane) & 1u) sm.rec[kIdExt + 32u + lane] = wt_resolve_entry(desc, t, lane + 32u, ep);
-        if (lane == 0) sm.rec[kIdExt + 64u] = wt_resolve_entry(desc, t, 64u, ep);  // prev: nearly every tile reads it
+        if ((need_lo >> lane) & 1u) sm.rec[kIdExt + lane] = wt_resolve_entry(desc, t, lane, ep, init);
+        if ((need_hi >> lane) & 1u) sm.rec[kIdExt + 32u + lane] = wt_resolve_entry(desc, t, lane + 32u, ep, init);
+        if (lane == 0) sm.rec[kIdExt + 64u] = wt_resolve_entry(desc, t, 64u, ep, init);  // prev: nearly every tile reads it
         __syncwarp();
         // now-known entries become inclusive words, so later tiles stop here
 #pragma unroll
@@ -866,6 +922,13 @@ namespace qb
                     pub_add[hh] = add4(pub_add[hh], sm.rec[kIdExt + pub_ref[hh]]);
                     st_word(desc + kDwState + e, pack_word((uint64_t)pub_ref[hh] << 32 | pub_add[hh], ST_INCL, epoch));  // value; the entry it came from stays readable
                 }
+            }
+        }
+        if constexpr (kStream) {
+            if (final_tile) {
+#pragma unroll
+                for (int hh = 0; hh < 3; ++hh) fin_val[hh] = pub_add[hh];  // every entry is resolved here: the state after the last consumed op
+                fin_rem = run_rem, fin_made = final_made, fin_used = final_used, fin_final = true;
             }
         }
         // entry nodes and OP_INDEX ops become absolute
@@ -905,9 +968,9 @@ namespace qb
                     d[0] = (uint8_t)val, d[1] = (uint8_t)(val >> 8), d[2] = (uint8_t)(val >> 16);
                 }
             };
-            for (unsigned kb = 0; kb < n_ops; kb += 32u, recp += 32, basep += 32, slotp += 32) {
+            for (unsigned kb = 0; kb < n_keep; kb += 32u, recp += 32, basep += 32, slotp += 32) {
                 const unsigned k     = kb + lane;
-                const bool     valid = k < n_ops;
+                const bool     valid = k < n_keep;
                 unsigned       v = 0, sl = 0;
                 if (valid) {
                     v                = *recp;
@@ -980,6 +1043,20 @@ namespace qb
         }
         QB_STAMP(desc, 75, 1, qb_t0);  // emit
 
+        if constexpr (kStream) {
+            // ---- the final tile reports what the call consumed and produced and the state to carry on with (stream.cpp:418-423)
+            if (fin_final && !still_bad) {
+                res->state.table[lane] = fin_val[0], res->state.table[lane + 32] = fin_val[1];
+                if (lane == 0) {
+                    res->state.prev = fin_val[2], res->state.run = fin_rem;
+                    res->processed = fin_used;
+                    res->written   = fin_made * P.target;
+                    res->pixels    = fin_made;
+                }
+            }
+            __syncwarp();
+            return;
+        }
         // ---- the stream ended before the image: the zero padding decodes as INDEX 0 forever (simple.cpp:106,132-135)
         if (t == ntiles - 1) {
             const uint64_t have = pix_base_f + n_pix_f;
@@ -1023,6 +1100,22 @@ namespace qb
         }
     }
 
+    // resumable decode (StreamDecoder::decode): the same persistent warps over the tiles of one input buffer, carry-in P.init
+    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_wt_stream_kernel(const DecParams P)
+    {
+        uint2*         lut  = reinterpret_cast<uint2*>(QB_DYN_SMEM);
+        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM + kWtLutBytes)[threadIdx.x >> 5];
+        const unsigned lane = threadIdx.x & 31u;
+        wt_build_lut(lut);
+        for (;;) {
+            unsigned x = 0;
+            if (lane == 0) x = atomicAdd(&P.control->tickets[0], 1u);
+            x = __shfl_sync(kFull, x, 0);
+            if (x >= P.n_tiles) break;
+            wt_decode_tile<true>(P, sm, lut, 0u, x, 0u, x, P.n_tiles, P.qoi + P.single[0], P.single[1] - P.single[0], 0u);
+        }
+    }
+
     // =====================================================================================================
     // Exact sequential decoder: the reference loop (simple.cpp:100-171, stream.cpp:312-447) with one decoding lane per
     // image; the other 31 lanes stage input and output through shared memory.  Runs for images the retry rounds could not
@@ -1033,6 +1126,7 @@ namespace qb
         uint32_t        mode;      // 0 = redo images flagged bad; 1 = resumable decode of one buffer
         const DecState* init;      // mode 1 carry-in
         uint64_t        in_size;   // mode 1: bytes available (no header), out capacity in bytes is d.out_stride
+        uint32_t        only_if_bad;  // mode 1 behind decode_wt_stream_kernel: run only when that kernel refuted a speculation
     };
 
     constexpr int kSerIn = 4096, kSerOut = 1024;
@@ -1050,6 +1144,7 @@ namespace qb
         const unsigned        lane = threadIdx.x & 31u;
         DecResult*            res  = P.results + img;
         unsigned restart = 0;  // mode 0: first tile to decode again (the tiles before it verified in some round)
+        if (S.mode == 1 && S.only_if_bad && res->bad == 0) return;  // the parallel kernel's result stands
         if (S.mode == 0) {
             unsigned rounds = 0;
             for (int r = 0; r < kDecRounds; ++r)
@@ -1211,12 +1306,27 @@ namespace qb
         }
     }
 
+    // device-side epilogue of the *_stream_*_dev entry points: results of the call -> the caller's result and state blocks
+    struct StreamOut {
+        uint64_t processed, written;
+    };
+    __global__ void stream_decode_epilogue_kernel(const DecResult* res, StreamOut* out, DecState* state)
+    {
+        const unsigned i = threadIdx.x;
+        if (i < 64u) state->table[i] = res->state.table[i];
+        if (i == 0) state->prev = res->state.prev, state->run = res->state.run, out->processed = res->processed, out->written = res->written;
+    }
+
 #ifndef QB_EMU
     inline cudaError_t dec_set_attrs()
     {
         cudaError_t e = cudaFuncSetAttribute(decode_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_wt_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_wt_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;

@@ -191,6 +191,7 @@ struct qoipp_b200_ctx {
     bool     attrs_set   = false;
     uint32_t ts_ticket = 0;  // encode_ts_kernel: current value of its ticket counter
     bool     force_general = false;  // QOIPP_B200_GENERAL=1: always the general kernels (A/B measurements, tests)
+    uint64_t stream_parallel_min = 4 * kDecTB;  // resumable decode: shorter inputs take the sequential loop (QOIPP_B200_STREAM_PARALLEL_MIN)
     int      dec_coresident = 148;  // CTAs of decode_finish_kernel that fit on the device at once
 
     // reserves `count` consecutive epochs and returns with `epoch` = the first; the carry buffer (and the tagged
@@ -400,6 +401,13 @@ namespace
         return cudaSuccess;
     }
 
+    __global__ void stream_encode_epilogue_kernel(const EncResult* res, unsigned ch, StreamOut* out, EncState* state)
+    {
+        const unsigned i = threadIdx.x;
+        if (i < 64u) state->table[i] = res->state.table[i];
+        if (i == 0) state->prev = res->state.prev, state->run = res->state.run, out->processed = res->processed * ch, out->written = res->written;
+    }
+
     unsigned pack_px(const uint8_t* p) { return p[0] | (unsigned)p[1] << 8 | (unsigned)p[2] << 16 | (unsigned)p[3] << 24; }
     void     unpack_px(unsigned v, uint8_t* p) { p[0] = (uint8_t)v, p[1] = (uint8_t)(v >> 8), p[2] = (uint8_t)(v >> 16), p[3] = (uint8_t)(v >> 24); }
 }  // namespace
@@ -458,6 +466,7 @@ extern "C"
         }
         c->sm_count = prop.multiProcessorCount;
         if (const char* g = std::getenv("QOIPP_B200_GENERAL")) c->force_general = g[0] == '1';
+        if (const char* g = std::getenv("QOIPP_B200_STREAM_PARALLEL_MIN")) c->stream_parallel_min = (uint64_t)std::max(1ll, std::atoll(g));
         if (const char* g = std::getenv("QOIPP_B200_COPY_THREADS")) c->copy_threads = (unsigned)std::max(0, std::min(16, std::atoi(g)));
         c->copy_threads = std::min(c->copy_threads, std::max(1u, std::thread::hardware_concurrency()) - 1u);
         *out        = c;
@@ -617,6 +626,30 @@ extern "C"
         return 0;
     }
 
+    // ---- resumable encode on device buffers: everything is enqueued on `stream`, nothing waits for the device
+    int32_t qoipp_b200_stream_encode_dev(qoipp_b200_ctx* c, uint8_t channels, qoipp_b200_dev_state* d_state, const uint8_t* d_in,
+                                         uint64_t in_size, uint8_t* d_out, uint64_t out_cap, qoipp_b200_stream_result* d_result, void* stream)
+    {
+        if (channels != 3 && channels != 4) return H::NotInitialized;  // error order of StreamEncoder::encode, stream.cpp:140-146
+        if (out_cap == 0 || in_size == 0) return H::Empty;
+        if (out_cap < 5) return H::TooShort;
+        const uint64_t n = in_size / channels;  // whole pixels only (stream.cpp:59)
+        Guard g(c->device);
+        auto  s = static_cast<cudaStream_t>(stream);
+        if (n == 0) {
+            QB_CUDA(cudaMemsetAsync(d_result, 0, sizeof(*d_result), s));
+            return 0;
+        }
+        const uint64_t cap = std::min<uint64_t>(out_cap, n * (channels + 1) + 1);  // worst case of this input + a pending run flush
+        c->enc_trivial = false;
+        if (int32_t e = launch_encode(c, d_in, 0, 1, n, channels, nullptr, d_out, 0, cap, ENC_STREAM, reinterpret_cast<const EncState*>(d_state), s))
+            return e;
+        stream_encode_epilogue_kernel<<<1, 64, 0, s>>>(static_cast<const EncResult*>(c->results.p), channels, reinterpret_cast<StreamOut*>(d_result),
+                                                       reinterpret_cast<EncState*>(d_state));
+        QB_CUDA(cudaGetLastError());
+        return 0;
+    }
+
     int32_t qoipp_b200_stream_encode_host(qoipp_b200_ctx* c, qoipp_b200_state* st, const uint8_t* h_in, uint64_t in_size,
                                           uint8_t* h_out, uint64_t out_cap, uint64_t* processed, uint64_t* written)
     {
@@ -634,28 +667,27 @@ extern "C"
         cudaStream_t s  = c->own_stream;
         QB_CUDA(c->stage_in.reserve(n * ch + 16, s));
         QB_CUDA(c->stage_out.reserve(cap + 16, s));
-        QB_CUDA(c->state.reserve(sizeof(EncState), s));
-        auto*        hs = reinterpret_cast<EncState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
+        QB_CUDA(c->state.reserve(sizeof(EncState) + sizeof(StreamOut), s));
+        auto* d_state = static_cast<EncState*>(c->state.p);
+        auto* d_sres  = reinterpret_cast<StreamOut*>(d_state + 1);
+        auto* hs = reinterpret_cast<EncState*>(static_cast<uint8_t*>(c->h_result.p) + 1024);
         hs->prev = pack_px(st->prev), hs->run = st->run;
         for (int i = 0; i < 64; ++i) hs->table[i] = pack_px(st->seen[i]);
-        QB_CUDA(cudaMemcpyAsync(c->state.p, hs, sizeof(EncState), cudaMemcpyHostToDevice, s));
-        QB_CUDA(cudaMemcpyAsync(c->stage_in.p, h_in, n * ch, cudaMemcpyHostToDevice, s));
-        c->enc_trivial = false;
-        if (int32_t e = launch_encode(c, static_cast<uint8_t*>(c->stage_in.p), 0, 1, n, ch, nullptr, static_cast<uint8_t*>(c->stage_out.p),
-                                      0, cap, ENC_STREAM, static_cast<EncState*>(c->state.p), s))
+        QB_CUDA(cudaMemcpyAsync(d_state, hs, sizeof(EncState), cudaMemcpyHostToDevice, s));
+        QB_CUDA(pageable_to_device(c, c->stage_in.p, h_in, n * ch, s));
+        if (int32_t e = qoipp_b200_stream_encode_dev(c, (uint8_t)ch, reinterpret_cast<qoipp_b200_dev_state*>(d_state), static_cast<uint8_t*>(c->stage_in.p), n * ch,
+                                                     static_cast<uint8_t*>(c->stage_out.p), cap, reinterpret_cast<qoipp_b200_stream_result*>(d_sres), s))
             return e;
-        auto* hr = static_cast<EncResult*>(c->h_result.p);
-        QB_CUDA(cudaMemcpyAsync(hr, c->results.p, sizeof(EncResult), cudaMemcpyDeviceToHost, s));
+        auto* hr = reinterpret_cast<EncState*>(static_cast<uint8_t*>(c->h_result.p) + 2048);
+        QB_CUDA(cudaMemcpyAsync(hr, d_state, sizeof(EncState) + sizeof(StreamOut), cudaMemcpyDeviceToHost, s));
         QB_CUDA(cudaStreamSynchronize(s));
-        if (hr->written) {
-            QB_CUDA(cudaMemcpyAsync(h_out, c->stage_out.p, hr->written, cudaMemcpyDeviceToHost, s));
-            QB_CUDA(cudaStreamSynchronize(s));
-        }
-        *processed = hr->processed * ch;
-        *written   = hr->written;
-        unpack_px(hr->state.prev, st->prev);
-        st->run = (uint8_t)hr->state.run;
-        for (int i = 0; i < 64; ++i) unpack_px(hr->state.table[i], st->seen[i]);
+        const auto* ho = reinterpret_cast<const StreamOut*>(hr + 1);
+        if (ho->written) QB_CUDA(device_to_pageable(c, h_out, c->stage_out.p, ho->written, s));
+        *processed = ho->processed;
+        *written   = ho->written;
+        unpack_px(hr->prev, st->prev);
+        st->run = (uint8_t)hr->run;
+        for (int i = 0; i < 64; ++i) unpack_px(hr->table[i], st->seen[i]);
         return 0;
     }
 }

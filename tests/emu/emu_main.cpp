@@ -155,17 +155,36 @@ extern "C"
         return 0;
     }
 
+    // resumable decode.  parallel != 0: decode_wt_stream_kernel first (whatever the input size), the sequential loop only
+    // when that kernel refuted a speculation -- the launch sequence of qoipp_b200_stream_decode_dev.  *used_serial reports which.
     int emu_stream_decode(qoipp_b200_state* st, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t cap,
-                          uint64_t* processed, uint64_t* written)
+                          uint64_t* processed, uint64_t* written, int parallel, int resident, uint64_t seed, int* used_serial)
     {
         DecState is{};
         is.prev = pack(st->prev); is.run = st->run;
         for (int s = 0; s < 64; ++s) is.table[s] = pack(st->seen[s]);
+        const unsigned ch = st->channels;
         DecResult    res{};
+        DecControl   ctl;
+        memset(&ctl, 0, sizeof ctl);
         SerialParams S{};
-        S.d.qoi = in; S.d.single[0] = 0; S.d.single[1] = in_size; S.d.out = out; S.d.out_stride = cap;
-        S.d.target = st->channels; S.d.flip = 0; S.d.n_images = 1; S.d.results = &res;
-        S.mode = 1; S.init = &is; S.in_size = in_size;
+        const uint64_t room = cap / ch;
+        S.d.qoi = in; S.d.single[0] = 0; S.d.single[1] = in_size; S.d.out = out; S.d.out_stride = room * ch;
+        S.d.target = ch; S.d.flip = 0; S.d.n_images = 1; S.d.results = &res; S.d.n_pixels = room;
+        S.mode = 1; S.init = &is; S.in_size = in_size; S.only_if_bad = 0;
+        const uint64_t tiles = (in_size + kDecTB - 1) / kDecTB;
+        std::vector<uint64_t> desc((size_t)tiles * kDecDescWords + 1, 0);
+        std::vector<uint32_t> fix((size_t)tiles * kFixWords + 1, 0xDEADBEEFu);
+        if (parallel && tiles > 0) {
+            DecParams& P = S.d;
+            P.offsets = nullptr; P.tile_first = nullptr; P.n_tiles = (uint32_t)tiles; P.epoch = 7; P.round = 0;
+            P.control = &ctl; P.desc = desc.data(); P.fix = fix.data(); P.init = &is;
+            const unsigned n_ctas = std::max(1u, std::min<unsigned>((P.n_tiles + kWtWarps - 1) / kWtWarps, (unsigned)resident));
+            const DecParams PP = P;
+            emu::launch(dim3(n_ctas), dim3(kWtThreads), kWtSmemBytes + 128, [=] { decode_wt_stream_kernel(PP); }, (int)n_ctas, seed);
+            S.only_if_bad = 1;
+        }
+        if (used_serial) *used_serial = !(parallel && tiles > 0) || res.bad != 0;
         emu::launch(dim3(1), dim3(32), sizeof(SerialSmem) + 128, [=] { decode_serial_kernel(S); }, 1, 0);
         *processed = res.processed; *written = res.written;
         unpack(res.state.prev, st->prev);

@@ -113,7 +113,8 @@ def _setup_decode():
     L = lib()
     L.emu_decode.argtypes = [u8p, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8, C.c_int, u8p, C.c_uint64,
                              C.POINTER(C.c_int), C.c_int, C.c_int, C.c_uint64]
-    L.emu_stream_decode.argtypes = [C.POINTER(State), u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.emu_stream_decode.argtypes = [C.POINTER(State), u8p, C.c_uint64, u8p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int, C.c_int,
+                                    C.c_uint64, C.POINTER(C.c_int)]
     return L
 
 
@@ -152,8 +153,11 @@ def decode(qoi_list, w, h, target, flip=False, force_serial=False, resident=4, s
 
 
 class StreamDecoder:
-    def __init__(self):
+    def __init__(self, parallel=False, resident=3, seed=0):
+        """parallel: decode_wt_stream_kernel for every call (the device library does so from a few KB on)"""
         self.s = State()
+        self.parallel, self.resident, self.seed = parallel, resident, seed
+        self.serial_calls = 0
         self.reset()
 
     def reset(self):
@@ -182,8 +186,11 @@ class StreamDecoder:
         L = _setup_decode()
         p, n = C.c_uint64(0), C.c_uint64(0)
         inp = np.ascontiguousarray(inp)
+        used = C.c_int(0)
         L.emu_stream_decode(C.byref(self.s), _p(inp) if inp.size else _p(np.zeros(1, np.uint8)), inp.size, _p(out), out.size,
-                            C.byref(p), C.byref(n))
+                            C.byref(p), C.byref(n), int(self.parallel), self.resident, self.seed, C.byref(used))
+        self.serial_calls += used.value
+        self.seed += 1
         return 0, p.value, n.value
 
     def has_run_count(self):

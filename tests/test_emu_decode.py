@@ -186,3 +186,50 @@ def test_restart_of_the_sequential_kernel_mid_stream():
     ref = Oracle.decode(bad, 3)
     px, path = E.decode(bad, w, h, 3, seed=2)
     assert np.array_equal(px[0], ref), path
+
+
+@pytest.mark.parametrize("ch", [3, 4])
+def test_parallel_stream_decoder_sweep(ch):
+    """stream_test.cpp:204-252 with the tile kernel behind every call (the device library uses it from a few KB on)."""
+    f = FX[ch]
+    dec = E.StreamDecoder(parallel=True)
+    for size in list(range(5, 24)) + list(range(24, 1025, 53)):
+        for target in (0, 3, 4):
+            px, desc = H.stream_decode(dec, size, f["qoi"], target)
+            assert np.array_equal(px, H.retarget(f["raw"], ch, target)), (size, target)
+        px, _ = H.stream_decode(dec, size, f["qoi_incomplete"])
+        assert px.size != f["raw"].size and np.array_equal(px, f["raw"][: px.size]), size
+
+
+def test_parallel_stream_decoder_state_by_state():
+    """Random input / output sizes over multi-tile streams: (processed, written), the pixels and the complete carried state
+    equal the oracle's after every call -- capacity cuts inside tiles and runs, incomplete ops at the end of the input,
+    pending runs longer than the output, tiles behind the cut."""
+    rng = np.random.default_rng(18)
+    serial = calls = 0
+    for it in range(36):
+        kind = synth.CLASSES[it % len(synth.CLASSES)]
+        ch = 3 + (it & 1)
+        w, h = int(rng.integers(20, 160)), int(rng.integers(10, 90))
+        raw = synth.generate(kind, w, h, ch, seed=900 + it)
+        q = Oracle.encode(raw, w, h, ch)
+        a, b = E.StreamDecoder(parallel=True, resident=int(rng.integers(1, 4)), seed=it), Oracle.StreamDecoder()
+        tgt = [0, 3, 4][it % 3]
+        assert a.initialize(q[:14], tgt)[0] == 0 and b.initialize(q[:14], tgt)[0] == 0
+        off = 14
+        big = it % 3 == 0
+        for _ in range(10000):
+            if off >= q.size:
+                break
+            cap = int(rng.integers(4, 300)) if not big else int(rng.integers(2000, 40000))
+            take = int(rng.integers(1, 200)) if not big else int(rng.integers(500, 9000))
+            oa, ob = np.full(cap + 16, 0xAA, np.uint8), np.full(cap + 16, 0xAA, np.uint8)
+            ra, rb = a.decode(oa[:cap], q[off: off + take]), b.decode(ob[:cap], q[off: off + take])
+            assert ra == rb, (kind, ch, off, cap, take, ra, rb)
+            assert np.array_equal(oa[: ra[2]], ob[: rb[2]]), (kind, ch, off, cap, take)
+            assert (oa[cap:] == 0xAA).all()
+            assert a.s.run == b.s.run and bytes(a.s.prev) == bytes(b.s.prev) and bytes(a.s.seen) == bytes(b.s.seen), (kind, ch, off, cap, take)
+            off += ra[1]
+            calls += 1
+        serial += a.serial_calls
+    assert serial < calls / 2, (serial, calls)  # the tile kernel's result stands for most calls
