@@ -264,7 +264,9 @@ extern "C"
             const unsigned n_ctas = std::max(1u, std::min<unsigned>(want, (unsigned)c->dec_coresident));
             decode_wt_stream_kernel<<<n_ctas, kWtThreads, kWtSmemBytes, s>>>(P);
             QB_CUDA(cudaGetLastError());
-            S.only_if_bad = 1;  // the sequential loop behind it runs only if a speculation was refuted
+            void* args[] = { &P };  // the retry rounds (returns at once when round 0 verified every tile)
+            QB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_finish_stream_kernel), dim3(n_ctas), dim3(kWtThreads), args, kWtSmemBytes, s));
+            S.only_if_bad = 1;  // the sequential loop runs only for what the last round still refutes
         }
         decode_serial_kernel<<<1, 32, sizeof(SerialSmem), s>>>(S);
         QB_CUDA(cudaGetLastError());

@@ -1126,7 +1126,7 @@ namespace qb
         uint32_t        mode;      // 0 = redo images flagged bad; 1 = resumable decode of one buffer
         const DecState* init;      // mode 1 carry-in
         uint64_t        in_size;   // mode 1: bytes available (no header), out capacity in bytes is d.out_stride
-        uint32_t        only_if_bad;  // mode 1 behind decode_wt_stream_kernel: run only when that kernel refuted a speculation
+        uint32_t        only_if_bad;  // mode 1 behind the parallel kernels: run only when the last retry round still refuted a speculation
     };
 
     constexpr int kSerIn = 4096, kSerOut = 1024;
@@ -1144,7 +1144,7 @@ namespace qb
         const unsigned        lane = threadIdx.x & 31u;
         DecResult*            res  = P.results + img;
         unsigned restart = 0;  // mode 0: first tile to decode again (the tiles before it verified in some round)
-        if (S.mode == 1 && S.only_if_bad && res->bad == 0) return;  // the parallel kernel's result stands
+        if (S.mode == 1 && S.only_if_bad && res->first_bad[kDecRounds] == 0) return;  // the parallel kernels' result stands
         if (S.mode == 0) {
             unsigned rounds = 0;
             for (int r = 0; r < kDecRounds; ++r)
@@ -1273,7 +1273,8 @@ namespace qb
     // verified costs a single empty launch): rounds 1..kDecRounds re-decode, per image, the tiles from the first refuted
     // one on with the alphas learned by the round before (grid-wide barrier between rounds); what still fails after the
     // last round is decoded by the sequential loop, one warp per image, resuming behind the last verified tile.
-    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_finish_kernel(const DecParams P)
+    template <bool kStream>
+    __device__ __forceinline__ void decode_finish_body(const DecParams& P)
     {
         uint2*         lut  = reinterpret_cast<uint2*>(QB_DYN_SMEM);
         WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM + kWtLutBytes)[threadIdx.x >> 5];
@@ -1293,18 +1294,23 @@ namespace qb
                 locate_image(P, x, img, t, ntiles, stream, size);
                 const unsigned fb = P.results[img].first_bad[round - 1];
                 if (fb == 0 || t < 0xFFFFFFFFu - fb) continue;  // image verified, or a tile before the first refuted one: final
-                wt_decode_tile(P, sm, lut, round, x, img, t, ntiles, stream, size, 0xFFFFFFFFu - fb);
+                wt_decode_tile<kStream>(P, sm, lut, round, x, img, t, ntiles, stream, size, 0xFFFFFFFFu - fb);
             }
             QB_GRID_SYNC();
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            SerialParams S{};
-            S.d = P, S.mode = 0;
-            for (unsigned img = blockIdx.x; img < P.n_images; img += gridDim.x)
-                decode_serial_body(S, *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM), img);
+        if constexpr (!kStream) {
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                SerialParams S{};
+                S.d = P, S.mode = 0;
+                for (unsigned img = blockIdx.x; img < P.n_images; img += gridDim.x)
+                    decode_serial_body(S, *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM), img);
+            }
         }
     }
+    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_finish_kernel(const DecParams P) { decode_finish_body<false>(P); }
+    // resumable decode: the retry rounds only; what the last round still refutes is decoded by decode_serial_kernel (mode 1) behind it
+    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_finish_stream_kernel(const DecParams P) { decode_finish_body<true>(P); }
 
     // device-side epilogue of the *_stream_*_dev entry points: results of the call -> the caller's result and state blocks
     struct StreamOut {
@@ -1323,6 +1329,10 @@ namespace qb
         cudaError_t e = cudaFuncSetAttribute(decode_wt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(decode_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_finish_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_finish_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(decode_wt_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWtSmemBytes);
         if (e != cudaSuccess) return e;

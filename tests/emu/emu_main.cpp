@@ -182,9 +182,10 @@ extern "C"
             const unsigned n_ctas = std::max(1u, std::min<unsigned>((P.n_tiles + kWtWarps - 1) / kWtWarps, (unsigned)resident));
             const DecParams PP = P;
             emu::launch(dim3(n_ctas), dim3(kWtThreads), kWtSmemBytes + 128, [=] { decode_wt_stream_kernel(PP); }, (int)n_ctas, seed);
+            emu::launch(dim3(n_ctas), dim3(kWtThreads), kWtSmemBytes + 128, [=] { decode_finish_stream_kernel(PP); }, (int)n_ctas, seed + 1);
             S.only_if_bad = 1;
         }
-        if (used_serial) *used_serial = !(parallel && tiles > 0) || res.bad != 0;
+        if (used_serial) *used_serial = !(parallel && tiles > 0) || res.first_bad[kDecRounds] != 0;
         emu::launch(dim3(1), dim3(32), sizeof(SerialSmem) + 128, [=] { decode_serial_kernel(S); }, 1, 0);
         *processed = res.processed; *written = res.written;
         unpack(res.state.prev, st->prev);
