@@ -735,7 +735,14 @@ namespace qb
         const uint64_t pix_base = (uint64_t)pin.hi << 32 | pin.lo;
         const unsigned ain      = pin.a & 255u;
         if (lane == 0) sm.rec[kIdAbsA] = ain << 24;
-        unsigned n_keep = n_ops;  // ops of this tile that are executed (all of them, except in the final tile of a resumable decode)
+        // ops of this tile that are executed: all of them, except in the final tile of a resumable decode.  (A second variable
+        // beside n_ops in the one-shot instantiation cost 18 % of the 8K decode: registers across the whole tile body.)
+        [[maybe_unused]] unsigned n_keep_s = n_ops;
+        auto n_keep = [&]() -> unsigned {
+            if constexpr (kStream) return n_keep_s;
+            else return n_ops;
+        };
+        // ops of this tile that are executed (all of them, except in the final tile of a resumable decode)
         [[maybe_unused]] bool     final_tile = false;
         [[maybe_unused]] unsigned run_rem = 0, final_endp = 0;
         [[maybe_unused]] uint64_t final_made = 0, final_used = 0;  // pixels in the output / input bytes consumed when this is the final tile
@@ -745,13 +752,16 @@ namespace qb
                 const uint64_t pre = (uint64_t)init->run < N ? (uint64_t)init->run : N;
                 for (uint64_t q = lane; q < pre; q += 32u) store_pixel(out, q, init->prev, P);
             }
-            // only the last op of the whole input can be incomplete: it is left for the next call
-            const bool     incomplete = __ballot_sync(kFull, t == ntiles - 1u && nops != 0 && exit_p > limit) != 0;
+            // Only the last op of the whole input can be incomplete; it is left for the next call.  It may START in the tile before
+            // the last one and reach past the end of the input through the last tile, which then has nothing to decode.
+            const uint64_t avail = body_len - tile_b0;
+            if ((uint64_t)tile_entry > avail) return;
+            const bool incomplete = __ballot_sync(kFull, nops != 0 && (uint64_t)exit_p > avail) != 0;
             const unsigned keep_ops = n_ops - (incomplete ? 1u : 0u), keep_pix = n_pix - (incomplete ? 1u : 0u);
             if (pix_base >= N) {
                 if (t > 0) return;  // the output was full before this tile: nothing of it is consumed
-                final_tile = true, n_keep = 0, run_rem = (unsigned)(pix_base - N), final_made = N, final_used = 0;  // not even the pending run fits
-            } else if (pix_base + keep_pix >= N || t == ntiles - 1u) {
+                final_tile = true, n_keep_s = 0, run_rem = (unsigned)(pix_base - N), final_made = N, final_used = 0;  // not even the pending run fits
+            } else if (pix_base + keep_pix >= N || incomplete || t == ntiles - 1u) {
                 final_tile = true;
                 // the op that holds the last pixel that fits (the output is the limit), else the last complete op (the input is)
                 const bool     by_room = pix_base + keep_pix >= N;
@@ -769,9 +779,9 @@ namespace qb
                 const unsigned who = __ballot_sync(kFull, hit);
                 if (who) {
                     const int src = __ffs((int)who) - 1;
-                    n_keep = __shfl_sync(kFull, kcut, src) + 1u, run_rem = __shfl_sync(kFull, rem, src), final_endp = __shfl_sync(kFull, endp, src);
+                    n_keep_s = __shfl_sync(kFull, kcut, src) + 1u, run_rem = __shfl_sync(kFull, rem, src), final_endp = __shfl_sync(kFull, endp, src);
                 } else {
-                    n_keep = 0, final_endp = tile_entry;  // no complete op starts in this tile
+                    n_keep_s = 0, final_endp = tile_entry;  // no complete op starts in this tile
                 }
                 final_made = by_room ? N : pix_base + keep_pix, final_used = tile_b0 + final_endp;
             }
@@ -783,7 +793,7 @@ namespace qb
         {
             const unsigned last_lane = 31u - (unsigned)__clz((int)(__ballot_sync(kFull, nops != 0) | 1u));
             const unsigned lb = __shfl_sync(kFull, exit_bid, (int)last_lane), lr = __shfl_sync(kFull, exit_rec, (int)last_lane);
-            prev_done = n_ops != 0 && lb == kIdAbs && n_keep == n_ops;
+            prev_done = n_ops != 0 && lb == kIdAbs && n_keep() == n_ops;
             if (prev_done && lane == 0) st_word(desc + kDwState + 64, pack_word((uint64_t)65u << 32 | lr, ST_INCL, epoch));
         }
         // entry nodes: the value entering lane l's chunk = the value of the op before its first one
@@ -846,7 +856,7 @@ namespace qb
         // here it is 32 ops per ~10.)
         {
             const unsigned hEl = sm.hE[lane], ownE = kIdE + lane, a11 = 11u * ain;
-            for (unsigned j = 0, k = opbase; j < nops && k < n_keep; ++j, ++k) {
+            for (unsigned j = 0, k = opbase; j < nops && (!kStream || k < n_keep()); ++j, ++k) {
                 const unsigned s8 = sm.slot[k];
                 if (s8 >= 0xC0u) continue;  // an OP_RUN repeats its predecessor: never the only writer of a slot
                 const unsigned b = sm.base[k];
@@ -875,8 +885,8 @@ namespace qb
             const unsigned e = lane + 32u * hh;
             pub_ref[hh] = 66u, pub_add[hh] = 0;
             if (e > 64u) continue;
-            const unsigned k = e < 64u ? (unsigned)sm.lastk[e] - 1u : n_keep - 1u;  // 0xFFFFFFFF = none
-            const bool     none = e < 64u ? sm.lastk[e] == 0 : n_keep == 0;
+            const unsigned k = e < 64u ? (unsigned)sm.lastk[e] - 1u : n_keep() - 1u;  // 0xFFFFFFFF = none
+            const bool     none = e < 64u ? sm.lastk[e] == 0 : n_keep() == 0;
             unsigned       ref = e, add = 0;
             if (!none) {
                 unsigned b = sm.base[k];
@@ -968,9 +978,9 @@ namespace qb
                     d[0] = (uint8_t)val, d[1] = (uint8_t)(val >> 8), d[2] = (uint8_t)(val >> 16);
                 }
             };
-            for (unsigned kb = 0; kb < n_keep; kb += 32u, recp += 32, basep += 32, slotp += 32) {
+            for (unsigned kb = 0; kb < n_keep(); kb += 32u, recp += 32, basep += 32, slotp += 32) {
                 const unsigned k     = kb + lane;
-                const bool     valid = k < n_keep;
+                const bool     valid = k < n_keep();
                 unsigned       v = 0, sl = 0;
                 if (valid) {
                     v                = *recp;

@@ -35,7 +35,11 @@ namespace qb::host
     {
         uint64_t n;
         if (int32_t e = count_bytes(d, &n)) return e;
-        *out = ((uint64_t)d.channels + 1) * d.width * d.height + kHeaderSize + kMarkerSize;
+        // (channels + 1) * width * height + 22 (common.hpp:394-412), refused when it does not fit 64 bits: the reference would
+        // hand back a wrapped value for such a descriptor; a capacity test against a wrapped value must never pass
+        const uint64_t px = (uint64_t)d.width * d.height, mul = (uint64_t)d.channels + 1;
+        if (px > (~0ull - (kHeaderSize + kMarkerSize)) / mul) return TooBig;
+        *out = mul * px + kHeaderSize + kMarkerSize;
         return Ok;
     }
 

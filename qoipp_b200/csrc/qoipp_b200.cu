@@ -271,7 +271,8 @@ namespace
         // buffers, the resumable form, unaligned spans -- takes the general kernel.  So do page-locked HOST buffers used in
         // place: the general kernel reads and writes in one pass, so both PCIe directions are busy at once, while the
         // encode + copy pair would use them one after the other (measured: 4K RGB e2e 37 GB/s against 27 GB/s).
-        const bool ts = flags == 0 && d_init == nullptr && out_cap >= n_pixels * (ch + 1) + H::kHeaderSize + H::kMarkerSize &&
+        const bool worst_fits = n_pixels <= (~0ull - (H::kHeaderSize + H::kMarkerSize)) / (ch + 1);  // no wrapped comparison below
+        const bool ts = flags == 0 && d_init == nullptr && worst_fits && out_cap >= n_pixels * (ch + 1) + H::kHeaderSize + H::kMarkerSize &&
                         (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0 && (n_images == 1 || (in_stride & 15u) == 0) &&
                         buffers_on_device && !c->force_general;
         const uint64_t T     = ts ? (uint64_t)kTsT : (uint64_t)kEncThreads * kEncK;
@@ -319,7 +320,12 @@ namespace
             if (ch == 3) encode_kernel<3, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
             else encode_kernel<4, kEncK><<<grid, dim3(kEncThreads), sizeof(EncSmem<kEncK>), s>>>(P);
         }
-        QB_CUDA(cudaGetLastError());
+        if (cudaError_t le = cudaGetLastError(); le != cudaSuccess) {
+            // the host-side shadow of the ticket counter was advanced for a launch that did not happen: start both from zero again
+            (void)cudaMemsetAsync(c->tickets.p, 0, 64, s);
+            c->ts_ticket = 0;
+            return cuda_code(le);
+        }
         return 0;
     }
 
@@ -534,7 +540,7 @@ extern "C"
         uint64_t need, worst;
         if (int32_t e = H::count_bytes(*desc, &need)) return e;
         if (raw_size != need) return H::MismatchedDesc;
-        H::worst_size(*desc, &worst);
+        if (int32_t e = H::worst_size(*desc, &worst)) return e;
         Guard          g(c->device);
         const uint64_t cap = std::min(out_cap, worst);
         cudaStream_t   s   = c->own_stream;
@@ -588,7 +594,7 @@ extern "C"
         if (n_images == 0) return H::Empty;
         if (raw_stride < raw || out_stride < out_cap) return H::MismatchedDesc;
         if (out_cap < H::kHeaderSize) return H::NotEnoughSpace;
-        H::worst_size(*desc, &worst);
+        if (int32_t e = H::worst_size(*desc, &worst)) return e;
         const uint64_t cap = std::min(out_cap, worst);
         Guard          g(c->device);
         cudaStream_t   s     = c->own_stream;

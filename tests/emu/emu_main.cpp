@@ -169,6 +169,11 @@ extern "C"
         memset(&ctl, 0, sizeof ctl);
         SerialParams S{};
         const uint64_t room = cap / ch;
+        // the kernels stage whole 16-byte aligned vectors: up to 15 bytes around the buffer are read (never across a page on
+        // the device); give the host copy that slack, at an odd alignment
+        std::vector<uint8_t> padded(in_size + 64, 0xEE);
+        memcpy(padded.data() + 19, in, in_size);
+        in = padded.data() + 19;
         S.d.qoi = in; S.d.single[0] = 0; S.d.single[1] = in_size; S.d.out = out; S.d.out_stride = room * ch;
         S.d.target = ch; S.d.flip = 0; S.d.n_images = 1; S.d.results = &res; S.d.n_pixels = room;
         S.mode = 1; S.init = &is; S.in_size = in_size; S.only_if_bad = 0;

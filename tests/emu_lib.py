@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
-SO = os.path.join(HERE, "libqb_emu.so")
+SO = os.environ.get("QB_EMU_SO", os.path.join(HERE, "libqb_emu.so"))  # tools/emu_asan.sh points this at the ASan + UBSan build
 u8p = C.POINTER(C.c_uint8)
 _lib = None
 

@@ -233,3 +233,24 @@ def test_parallel_stream_decoder_state_by_state():
             calls += 1
         serial += a.serial_calls
     assert serial < calls / 2, (serial, calls)  # the tile kernel's result stands for most calls
+
+
+def test_parallel_stream_decoder_incomplete_op_across_a_tile_boundary():
+    """RGBA noise: every op is 5 bytes, the op at byte 895 starts in tile 0 and ends in tile 1.  Inputs that end inside it
+    (896..899 bytes) must leave it for the next call although the tile that holds its first byte is not the last one."""
+    w, h = 40, 20
+    rng = np.random.default_rng(5)
+    body = rng.integers(0, 256, size=(w * h, 5), dtype=np.uint8)
+    body[:, 0] = 0xFF  # OP_RGBA r g b a, 800 times
+    body = body.reshape(-1)
+    q = np.concatenate([np.frombuffer(b"qoif" + w.to_bytes(4, "big") + h.to_bytes(4, "big") + bytes([4, 0]), dtype=np.uint8), body,
+                        np.array([0, 0, 0, 0, 0, 0, 0, 1], np.uint8)])
+    for n in list(range(888, 908)) + [1791, 1792, 1793, 1794, 1795, 1796]:
+        for cap in (100000, 4 * 150):
+            a, b = E.StreamDecoder(parallel=True), Oracle.StreamDecoder()
+            assert a.initialize(q[:14])[0] == 0 and b.initialize(q[:14])[0] == 0
+            oa, ob = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+            ra, rb = a.decode(oa, body[:n]), b.decode(ob, body[:n])
+            assert ra == rb, (n, cap, ra, rb)
+            assert np.array_equal(oa[: ra[2]], ob[: rb[2]])
+            assert bytes(a.s.prev) == bytes(b.s.prev) and bytes(a.s.seen) == bytes(b.s.seen) and a.s.run == b.s.run, (n, cap)
