@@ -40,6 +40,11 @@
 // (profiles/r02_experiments.md: 98 KB of SASS, hit rate 88 %, time proportional to the number of tiles whatever the
 // occupancy).  Helpers that are called once per tile, or are cold, are real calls instead of inlined copies.
 #define QB_NOINLINE __noinline__
+#ifdef QB_STATS  // development build: event counters in DecControl::pad (tools/stats_probe.py)
+#define QB_COUNT(P, i) do { if ((threadIdx.x & 31u) == 0) atomicAdd(&(P).control->pad[i], 1u); } while (0)
+#else
+#define QB_COUNT(P, i) do { } while (0)
+#endif
 #if defined(QB_EMU) || defined(QB_NO_REPAIR_FENCE)
 #define QB_FENCE_SC() do { } while (0)
 #else
@@ -97,7 +102,7 @@ namespace qb
 #define QB_WT_WARPS 4  // independent warp workers per CTA
 #endif
 #ifndef QB_WT_CTAS
-#define QB_WT_CTAS 5  // CTAs per SM the kernels are compiled for
+#define QB_WT_CTAS 6  // CTAs per SM the kernels are compiled for (<= 85 registers; 5 -> 6: 4K 193 -> 183 us, 8K 868 -> 838 us on the same build)
 #endif
     constexpr int kWtChunk = QB_WT_CHUNK, kDecTB = 32 * kWtChunk, kWtWarps = QB_WT_WARPS, kWtThreads = kWtWarps * 32;
     static_assert(kWtChunk >= 8 && kWtChunk <= 28 && kWtChunk % 4 == 0, "op-start masks are 32 bits wide");
@@ -467,7 +472,10 @@ namespace qb
             }
         }
         dlo = __reduce_or_sync(kFull, dlo), dhi = __reduce_or_sync(kFull, dhi), dprev = __reduce_or_sync(kFull, dprev), hard = __reduce_or_sync(kFull, hard);
+        QB_COUNT(P, 0);  // repaired tiles
         if (!(dlo | dhi | dprev | hard)) return;  // the repaired tile says exactly what it said before
+        if (hard) QB_COUNT(P, 1);
+        else if (dprev) QB_COUNT(P, 2);
         unsigned u = t + 1u;
 #ifdef QB_REPAIR_ALWAYS_REDO
         hard = 1;
@@ -501,7 +509,10 @@ namespace qb
             }
             if (u >= ntiles) return;  // the stream ended first
         }
-        if (u < ntiles) wt_flag_redo(P, round, res, u);
+        if (u < ntiles) {
+            if (!hard && !dprev) QB_COUNT(P, 3);  // a successor read a changed table entry / had not published / the scan gave up
+            wt_flag_redo(P, round, res, u);
+        }
     }
 
     // one tile (global ticket `gticket`) of round `round`; one warp.
@@ -917,7 +928,8 @@ namespace qb
         // pattern with a repairing predecessor (it republishes its words, then reads our need words, wt_repair_scan): without a
         // sequentially consistent fence on both sides each could miss the other's store -- we would use a retracted word and
         // the predecessor would not notice.
-        QB_FENCE_SC();
+        // (`prev` needs no fence: a predecessor whose `prev` changed sends everything behind it to the retry round, whatever was read.)
+        if (need_lo | need_hi) QB_FENCE_SC();
         if ((need_lo >> lane) & 1u) sm.rec[kIdExt + lane] = wt_resolve_entry(desc, t, lane, ep, init);
         if ((need_hi >> lane) & 1u) sm.rec[kIdExt + 32u + lane] = wt_resolve_entry(desc, t, lane + 32u, ep, init);
         if (lane == 0) sm.rec[kIdExt + 64u] = wt_resolve_entry(desc, t, 64u, ep, init);  // prev: nearly every tile reads it

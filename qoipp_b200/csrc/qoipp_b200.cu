@@ -700,6 +700,12 @@ extern "C"
 
 #include "decode_host.inl"
 
+#ifdef QB_STATS
+extern "C" int32_t qoipp_b200_debug_stats(qoipp_b200_ctx* c, uint32_t* out4)  // development aid only
+{
+    return cuda_code(cudaMemcpy(out4, static_cast<uint8_t*>(c->results.p) + offsetof(DecControl, pad), 16, cudaMemcpyDeviceToHost));
+}
+#endif
 #ifdef QB_TIMING
 extern "C" int32_t qoipp_b200_debug_carry(qoipp_b200_ctx* c, void** ptr, uint64_t* bytes)  // development aid only
 {
