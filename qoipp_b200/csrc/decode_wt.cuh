@@ -60,6 +60,7 @@ namespace qb
     };
 
     constexpr int kDecRounds = 4;  // verification-driven retry rounds before the sequential loop takes over
+    constexpr int kCascadeReqs = 7;  // cascade requests an image can hold; more of them send it to the retry rounds
 
     struct DecResult {
         uint32_t bad;   // round 0 refuted a speculation somewhere in this image
@@ -70,12 +71,17 @@ namespace qb
         uint32_t first_bad[kDecRounds + 1];  // per round: 0 = all verified, else 0xFFFFFFFF - first refuted tile
         uint32_t pad[3];
         DecState state;
+        // round 0 -> cascade (decode_finish_body): tiles that consumed a word their repaired predecessor retracted, each with the
+        // table entries / prev that had changed on entering it
+        uint32_t n_req, req_pad;
+        uint32_t req[kCascadeReqs][4];  // {tile, changed slots 0..31, 32..63, prev}
     };
 
     struct DecControl {  // zeroed with the results before every decode
         uint32_t tickets[kDecRounds + 1];  // tile tickets of round 0 and of the retry rounds
         uint32_t any_bad[kDecRounds + 1];  // some image needs round r + 1
-        uint32_t pad[4];
+        uint32_t rounds_needed;            // set by the cascade (decode_finish_body): some image still needs retry round 1
+        uint32_t pad[3];
     };
 
     struct DecParams {
@@ -99,10 +105,13 @@ namespace qb
 #define QB_WT_CHUNK 28  // stream bytes per lane: an odd number of words keeps the lanes' chunk reads on different banks
 #endif
 #ifndef QB_WT_WARPS
-#define QB_WT_WARPS 4  // independent warp workers per CTA
+#define QB_WT_WARPS 8  // warp workers per CTA
+#endif
+#ifndef QB_WT_LOCKSTEP
+#define QB_WT_LOCKSTEP 1  // the warps of a CTA start their tiles together (instruction cache, see decode_wt_kernel)
 #endif
 #ifndef QB_WT_CTAS
-#define QB_WT_CTAS 6  // CTAs per SM the kernels are compiled for (<= 85 registers; 5 -> 6: 4K 193 -> 183 us, 8K 868 -> 838 us on the same build)
+#define QB_WT_CTAS 3  // CTAs per SM the kernels are compiled for (24 warps, <= 85 registers)
 #endif
     constexpr int kWtChunk = QB_WT_CHUNK, kDecTB = 32 * kWtChunk, kWtWarps = QB_WT_WARPS, kWtThreads = kWtWarps * 32;
     static_assert(kWtChunk >= 8 && kWtChunk <= 28 && kWtChunk % 4 == 0, "op-start masks are 32 bits wide");
@@ -418,6 +427,24 @@ namespace qb
             P.control->any_bad[round] = 1;
         }
     }
+    // Table entries (and prev) whose value changed on the way into a tile
+    struct Changed {
+        unsigned lo, hi, prev;
+    };
+    // Round 0: a repaired tile found that tile `from` of its image consumed one of its retracted words.  The request is served
+    // after the round by the cascade of decode_finish_body: that tile alone is decoded again, then whatever read ITS changed
+    // words, ... -- a handful of tiles instead of everything behind it.  `c` = what had changed on entering `from`.
+    constexpr unsigned kCascadeFail = 0xFFFFFFFEu;
+    __device__ QB_NOINLINE void wt_flag_cascade(const DecParams& P, DecResult* res, unsigned from, const Changed& c)
+    {
+        if ((threadIdx.x & 31u) == 0) {
+            atomicOr(&res->bad, 2u);
+            const unsigned i = atomicAdd(&res->n_req, 1u);
+            if (i < (unsigned)kCascadeReqs) res->req[i][0] = from, res->req[i][1] = c.lo, res->req[i][2] = c.hi, res->req[i][3] = c.prev;
+            else atomicMax(&res->first_bad[0], 0xFFFFFFFFu - from);  // no room: everything from there on in the retry round
+            P.control->any_bad[0] = 1;
+        }
+    }
     __device__ QB_NOINLINE void wt_record_failures(const DecParams& P, WtSmem& sm, uint32_t* fix, const unsigned char* B, unsigned first_pos,
                                                    unsigned opbase, unsigned nops)
     {
@@ -451,13 +478,37 @@ namespace qb
     // entry a tile overwrites with a constant, or derives from an unchanged entry (the `ref` its state words keep), stops being
     // changed.  Usually nothing read the one or two table slots in question and they are overwritten within a tile or two.
     // A changed pixel / alpha or slot word is not followed (everything behind the tile is flagged).  Cold.  One warp.
-    __device__ QB_NOINLINE void wt_repair_scan(const DecParams& P, uint64_t* desc, unsigned t, unsigned ntiles, unsigned round, DecResult* res,
-                                               const Epochs& ep, const uint64_t (&old_word)[3], unsigned dirty)
+    // Returns the first tile behind t that has to be decoded again (kNoRedo: none; kCascadeFail | tile: the scan could not
+    // tell -- everything from that tile on).  `c`: in = entries that had already changed on entering t (a cascade carries them
+    // along; empty after a plain repair), out = the entries that have changed on entering the returned tile.
+    constexpr unsigned kScanGaveUp = 0x80000000u;
+    __device__ QB_NOINLINE unsigned wt_repair_scan(const DecParams& P, uint64_t* desc, unsigned t, unsigned ntiles, const Epochs& ep,
+                                                   const uint64_t (&old_word)[3], unsigned dirty, Changed& c)
     {
         constexpr unsigned kScan = 16;  // tiles followed before giving up
         const unsigned     lane  = threadIdx.x & 31u;
         unsigned dlo = 0, dhi = 0, dprev = 0, hard = 0;
         QB_FENCE_SC();  // this tile's republished words are ordered before the reads of the successors' need words (see wt_decode_tile)
+        // what tile u hands on of a changed set: an entry is still changed if it is derived from a changed one
+        auto hand_on = [&](const uint64_t* d_u, unsigned u, unsigned& lo, unsigned& hi, unsigned& pv) -> bool {
+            bool d[3];
+            bool missing = false;
+#pragma unroll
+            for (int hh = 0; hh < 3; ++hh) {
+                const unsigned e = lane + 32u * hh;
+                d[hh]            = false;
+                if (e <= 64u) {
+                    const uint64_t ws = ld_word(d_u + kDwState + e);
+                    if (!ep.valid(ws, u)) missing = true;
+                    const unsigned ref = (unsigned)(word_payload(ws) >> 32) & 0x7Fu;
+                    d[hh] = ref < 32u ? (lo >> ref) & 1u : (ref < 64u ? (hi >> (ref - 32u)) & 1u : (ref == 64u ? pv != 0 : false));
+                }
+            }
+            if (__ballot_sync(kFull, missing)) return false;
+            lo = __ballot_sync(kFull, d[0]), hi = __ballot_sync(kFull, d[1]), pv = __ballot_sync(kFull, d[2]) & 1u;
+            return true;
+        };
+        // (1) what this tile says differently from before
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const unsigned wi = 1u + 32u * i + lane;
@@ -472,47 +523,38 @@ namespace qb
             }
         }
         dlo = __reduce_or_sync(kFull, dlo), dhi = __reduce_or_sync(kFull, dhi), dprev = __reduce_or_sync(kFull, dprev), hard = __reduce_or_sync(kFull, hard);
+        // (2) what had changed before it and passes through it
+        if (c.lo | c.hi | c.prev) {
+            unsigned lo = c.lo, hi = c.hi, pv = c.prev;
+            if (!hand_on(desc, t, lo, hi, pv)) return kScanGaveUp | t;
+            dlo |= lo, dhi |= hi, dprev |= pv;
+        }
         QB_COUNT(P, 0);  // repaired tiles
-        if (!(dlo | dhi | dprev | hard)) return;  // the repaired tile says exactly what it said before
-        if (hard) QB_COUNT(P, 1);
-        else if (dprev) QB_COUNT(P, 2);
+        c = Changed{ dlo, dhi, dprev };
+        if (!(dlo | dhi | dprev | hard)) return kNoRedo;  // the repaired tile says exactly what it said before
+        if (hard || dprev) QB_COUNT(P, 1);
         unsigned u = t + 1u;
 #ifdef QB_REPAIR_ALWAYS_REDO
-        hard = 1;
+        return u < ntiles ? (kScanGaveUp | u) : kNoRedo;
 #endif
-        if (!hard) {
-            for (; u < ntiles && u <= t + kScan; ++u) {
-                const uint64_t* d_u = desc + (uint64_t)(u - t) * kDecDescWords;
-                // never wait here: tile u may not even have been drawn yet, and the warp that would draw it may be this one's
-                // neighbour stuck in the same scan.  A tile that has not said what it reads is decoded again.
-                const uint64_t wl = ld_word(d_u + kDwNeedLo), wh = ld_word(d_u + kDwNeedHi);
-                if (!ep.valid(wl, u) || !ep.valid(wh, u)) break;
-                const uint64_t nl = word_payload(wl), nh = word_payload(wh);
-                if (((unsigned)nl & dlo) | ((unsigned)nh & dhi) | dprev) break;  // tile u read a changed entry (prev is always read)
-                // what tile u hands on: an entry is still changed if it is derived from a changed one
-                bool d[3];
-                bool missing = false;
-#pragma unroll
-                for (int hh = 0; hh < 3; ++hh) {
-                    const unsigned e = lane + 32u * hh;
-                    d[hh]            = false;
-                    if (e <= 64u) {
-                        const uint64_t ws = ld_word(d_u + kDwState + e);
-                        if (!ep.valid(ws, u)) missing = true;
-                        const unsigned ref = (unsigned)(word_payload(ws) >> 32) & 0x7Fu;
-                        d[hh] = ref < 32u ? (dlo >> ref) & 1u : (ref < 64u ? (dhi >> (ref - 32u)) & 1u : (ref == 64u ? dprev != 0 : false));
-                    }
-                }
-                if (__ballot_sync(kFull, missing)) break;
-                dlo = __ballot_sync(kFull, d[0]), dhi = __ballot_sync(kFull, d[1]), dprev = __ballot_sync(kFull, d[2]) & 1u;
-                if (!(dlo | dhi | dprev)) return;  // every changed entry has been overwritten before anything read it
+        if (hard) return u < ntiles ? u : kNoRedo;  // a pixel / alpha or slot word changed: the next tile used it for certain
+        for (; u < ntiles && u <= t + kScan; ++u) {
+            const uint64_t* d_u = desc + (uint64_t)(u - t) * kDecDescWords;
+            // never wait here: tile u may not even have been drawn yet, and the warp that would draw it may be this one's
+            // neighbour stuck in the same scan.  A tile that has not said what it reads is decoded again, with all behind it.
+            const uint64_t wl = ld_word(d_u + kDwNeedLo), wh = ld_word(d_u + kDwNeedHi);
+            if (!ep.valid(wl, u) || !ep.valid(wh, u)) return kScanGaveUp | u;
+            const uint64_t nl = word_payload(wl), nh = word_payload(wh);
+            if (((unsigned)nl & dlo) | ((unsigned)nh & dhi) | dprev) {  // tile u read a changed entry (prev is always read)
+                QB_COUNT(P, 2);
+                c = Changed{ dlo, dhi, dprev };
+                return u;
             }
-            if (u >= ntiles) return;  // the stream ended first
+            if (!hand_on(d_u, u, dlo, dhi, dprev)) return kScanGaveUp | u;
+            if (!(dlo | dhi | dprev)) return kNoRedo;  // every changed entry has been overwritten before anything read it
         }
-        if (u < ntiles) {
-            if (!hard && !dprev) QB_COUNT(P, 3);  // a successor read a changed table entry / had not published / the scan gave up
-            wt_flag_redo(P, round, res, u);
-        }
+        if (u >= ntiles) return kNoRedo;  // the stream ended first
+        return kScanGaveUp | u;
     }
 
     // one tile (global ticket `gticket`) of round `round`; one warp.
@@ -521,10 +563,16 @@ namespace qb
     // output, an op that the input does not hold completely is not consumed (stream.cpp:341-392), and the tile that holds
     // the last consumed op ("final tile") reports bytes consumed, bytes written and the state to carry on with.  Tiles behind
     // it do nothing.  A refuted speculation is not retried here: the call falls back to the sequential loop.
+    // `cascade`: the tile is decoded AGAIN after round 0 (decode_finish_body) because a predecessor retracted a word it had
+    // consumed; everything around it is at rest.  Its carry words as they were count as "published before": what differs
+    // afterwards is followed through its successors like after a repair.  Returns the next tile to decode again (kNoRedo: none,
+    // kCascadeFail: this tile is still refuted -- the retry rounds take over); kNoRedo always outside a cascade.
     template <bool kStream = false>
-    __device__ __forceinline__ void wt_decode_tile(const DecParams& P, WtSmem& sm, const uint2* lut, unsigned round, unsigned gticket, unsigned img,
-                                                   unsigned t, unsigned ntiles, const uint8_t* stream, uint64_t size, unsigned fresh_from)
+    __device__ __forceinline__ unsigned wt_decode_tile(const DecParams& P, WtSmem& sm, const uint2* lut, unsigned round, unsigned gticket, unsigned img,
+                                                       unsigned t, unsigned ntiles, const uint8_t* stream, uint64_t size, unsigned fresh_from,
+                                                       Changed* casc = nullptr)
     {
+        const bool cascade = casc != nullptr;
         const unsigned lane = threadIdx.x & 31u;
         [[maybe_unused]] const long long qb_t0 = QB_T0();
         constexpr unsigned kSkip   = kStream ? 0u : kHeader;
@@ -635,6 +683,12 @@ namespace qb
         constexpr unsigned kRepairPasses = QB_REPAIR_PASSES;
         uint64_t           old_word[3] = { 0, 0, 0 };  // this lane's share of words 1 .. 67 as published by the latest refuted pass
         unsigned           dirty = 0;                  // bit i: word i of this lane differed between two refuted passes
+        if (cascade) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (1u + 32u * i + lane <= (unsigned)kDwState + 64u) old_word[i] = ld_word(desc + 1 + 32 * i + lane);
+            if (lane == 0) fix[0] = 0;  // alphas learned under the retracted inputs are not trusted
+        }
         uint64_t           pix_base_f = 0;
         unsigned           n_pix_f = 0, fixn0 = sm.fixn0;
         bool               tail_fill_f = false, still_bad = false;
@@ -766,11 +820,11 @@ namespace qb
             // Only the last op of the whole input can be incomplete; it is left for the next call.  It may START in the tile before
             // the last one and reach past the end of the input through the last tile, which then has nothing to decode.
             const uint64_t avail = body_len - tile_b0;
-            if ((uint64_t)tile_entry > avail) return;
+            if ((uint64_t)tile_entry > avail) return kNoRedo;
             const bool incomplete = __ballot_sync(kFull, nops != 0 && (uint64_t)exit_p > avail) != 0;
             const unsigned keep_ops = n_ops - (incomplete ? 1u : 0u), keep_pix = n_pix - (incomplete ? 1u : 0u);
             if (pix_base >= N) {
-                if (t > 0) return;  // the output was full before this tile: nothing of it is consumed
+                if (t > 0) return kNoRedo;  // the output was full before this tile: nothing of it is consumed
                 final_tile = true, n_keep_s = 0, run_rem = (unsigned)(pix_base - N), final_made = N, final_used = 0;  // not even the pending run fits
             } else if (pix_base + keep_pix >= N || incomplete || t == ntiles - 1u) {
                 final_tile = true;
@@ -1050,7 +1104,7 @@ namespace qb
         for (int i = 0; i < 3; ++i)  // a successor may have read the words of ANY refuted pass: a word counts as changed if two passes disagree on it
             if (1u + 32u * i + lane <= (unsigned)kDwState + 64u) {
                 const uint64_t now = ld_word(desc + 1 + 32 * i + lane);
-                if (pass > 0 && now != old_word[i]) dirty |= 1u << i;
+                if ((pass > 0 || cascade) && now != old_word[i]) dirty |= 1u << i;
                 old_word[i] = now;
             }
         __syncwarp();
@@ -1058,10 +1112,19 @@ namespace qb
         if (lane == 0) sm.fixn0 = fixn0, sm.nfail = 0;
         __syncwarp();
         }  // repair loop
+        unsigned next = kNoRedo;
         if (still_bad) {
-            wt_flag_redo(P, round, res, t);  // the image is eligible for the next round, from this tile on
-        } else if (pass) {  // repaired: did anything this tile told the others change, and did it matter?
-            wt_repair_scan(P, desc, t, ntiles, round, res, ep, old_word, dirty);
+            if (cascade) next = kCascadeFail;
+            else wt_flag_redo(P, round, res, t);  // the image is eligible for the next round, from this tile on
+        } else if (pass || cascade) {  // repaired / decoded again: did anything this tile told the others change, and did it matter?
+            Changed c{ 0u, 0u, 0u };
+            if (cascade) c = *casc;
+            const unsigned nx = wt_repair_scan(P, desc, t, ntiles, ep, old_word, dirty, c);
+            if (nx != kNoRedo) {
+                if (cascade) next = nx, *casc = c;  // the caller goes on there (or gives up: kScanGaveUp)
+                else if (round == 0 && !(nx & kScanGaveUp)) wt_flag_cascade(P, res, nx, c);
+                else wt_flag_redo(P, round, res, nx & ~kScanGaveUp);
+            }
         }
         QB_STAMP(desc, 75, 1, qb_t0);  // emit
 
@@ -1077,7 +1140,7 @@ namespace qb
                 }
             }
             __syncwarp();
-            return;
+            return next;
         }
         // ---- the stream ended before the image: the zero padding decodes as INDEX 0 forever (simple.cpp:106,132-135)
         if (t == ntiles - 1) {
@@ -1099,44 +1162,56 @@ namespace qb
             }
         }
         __syncwarp();
+        return next;
     }
 
-    // round 0: persistent, independent warps draw tiles from a ticket counter in start order, so every tile a running warp
-    // waits for is held by a warp that is running too or done
-    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_wt_kernel(const DecParams P)
+    template <bool kStream>
+    __device__ __forceinline__ void wt_round0(const DecParams& P)
     {
-        uint2*         lut  = reinterpret_cast<uint2*>(QB_DYN_SMEM);
-        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM + kWtLutBytes)[threadIdx.x >> 5];
-        const unsigned lane = threadIdx.x & 31u;
+        uint2*  lut = reinterpret_cast<uint2*>(QB_DYN_SMEM);
+        WtSmem& sm  = reinterpret_cast<WtSmem*>(QB_DYN_SMEM + kWtLutBytes)[threadIdx.x >> 5];
         wt_build_lut(lut);
+#if QB_WT_LOCKSTEP
+        // The warps of a CTA draw kWtWarps consecutive tiles together and start them together: the tile body is ~90 KB of
+        // straight-line code, far more than the 32 KB instruction cache of an SM, and warps that drift apart each keep their own
+        // part of it in flight ("no instruction" was the largest stall of the kernel: 2.8 of 11 stall cycles per issued
+        // instruction, 4.9 after the tile body had grown by 4 %).  Measured, 8K RGBA: independent warps 824 us, 4 / 8 / 12 warps
+        // in step 698 / 631 / 620 us; barriers INSIDE the tile (after staging, look-back 1, the walk, look-back 3, the state
+        // look-back) gain nothing more.  No tile waits for a warp of its own CTA at the barrier while that warp waits for one
+        // of its words: every word a tile owes its successors is published before the tile ends.
+        unsigned* base = reinterpret_cast<unsigned*>(QB_DYN_SMEM + kWtLutBytes + sizeof(WtSmem) * kWtWarps);
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) *base = atomicAdd(&P.control->tickets[0], (unsigned)kWtWarps);
+            __syncthreads();
+            const unsigned x0 = *base;
+            if (x0 >= P.n_tiles) break;
+            const unsigned x = x0 + (threadIdx.x >> 5);
+            if (x >= P.n_tiles) continue;
+#else
+        const unsigned lane = threadIdx.x & 31u;
         for (;;) {
             unsigned x = 0;
             if (lane == 0) x = atomicAdd(&P.control->tickets[0], 1u);
             x = __shfl_sync(kFull, x, 0);
             if (x >= P.n_tiles) break;
-            unsigned       img, t, ntiles;
-            const uint8_t* stream;
-            uint64_t       size;
-            locate_image(P, x, img, t, ntiles, stream, size);
-            wt_decode_tile(P, sm, lut, 0u, x, img, t, ntiles, stream, size, 0u);
+#endif
+            if constexpr (kStream) {
+                wt_decode_tile<true>(P, sm, lut, 0u, x, 0u, x, P.n_tiles, P.qoi + P.single[0], P.single[1] - P.single[0], 0u);
+            } else {
+                unsigned       img, t, ntiles;
+                const uint8_t* stream;
+                uint64_t       size;
+                locate_image(P, x, img, t, ntiles, stream, size);
+                wt_decode_tile<false>(P, sm, lut, 0u, x, img, t, ntiles, stream, size, 0u);
+            }
         }
     }
-
-    // resumable decode (StreamDecoder::decode): the same persistent warps over the tiles of one input buffer, carry-in P.init
-    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_wt_stream_kernel(const DecParams P)
-    {
-        uint2*         lut  = reinterpret_cast<uint2*>(QB_DYN_SMEM);
-        WtSmem&        sm   = reinterpret_cast<WtSmem*>(QB_DYN_SMEM + kWtLutBytes)[threadIdx.x >> 5];
-        const unsigned lane = threadIdx.x & 31u;
-        wt_build_lut(lut);
-        for (;;) {
-            unsigned x = 0;
-            if (lane == 0) x = atomicAdd(&P.control->tickets[0], 1u);
-            x = __shfl_sync(kFull, x, 0);
-            if (x >= P.n_tiles) break;
-            wt_decode_tile<true>(P, sm, lut, 0u, x, 0u, x, P.n_tiles, P.qoi + P.single[0], P.single[1] - P.single[0], 0u);
-        }
-    }
+    // round 0: persistent warps draw tiles from a ticket counter in start order, so every tile a running warp waits for is
+    // held by a warp that is running too or done
+    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_wt_kernel(const DecParams P) { wt_round0<false>(P); }
+    // resumable decode (StreamDecoder::decode): the same over the tiles of one input buffer, carry-in P.init
+    __global__ void __launch_bounds__(kWtThreads, QB_WT_CTAS) decode_wt_stream_kernel(const DecParams P) { wt_round0<true>(P); }
 
     // =====================================================================================================
     // Exact sequential decoder: the reference loop (simple.cpp:100-171, stream.cpp:312-447) with one decoding lane per
@@ -1288,7 +1363,7 @@ namespace qb
         decode_serial_body(S, *reinterpret_cast<SerialSmem*>(QB_DYN_SMEM), 0u);
     }
 
-    constexpr size_t kWtSmemBytes = kWtLutBytes + (sizeof(WtSmem) * kWtWarps > sizeof(SerialSmem) ? sizeof(WtSmem) * kWtWarps : sizeof(SerialSmem));
+    constexpr size_t kWtSmemBytes = kWtLutBytes + (sizeof(WtSmem) * kWtWarps > sizeof(SerialSmem) ? sizeof(WtSmem) * kWtWarps : sizeof(SerialSmem)) + 16;
     static_assert(sizeof(WtSmem) % 16 == 0, "per-warp areas stay 16-byte aligned");
 
     // Everything after round 0, in ONE cooperative launch of co-resident persistent CTAs (so that an image that
@@ -1303,8 +1378,64 @@ namespace qb
         const unsigned lane = threadIdx.x & 31u;
         if (P.control->any_bad[0] == 0 && P.control->any_bad[kDecRounds] == 0) return;  // everything verified in round 0 (same value in every CTA)
         wt_build_lut(lut);
+        // ---- cascade: tiles that consumed a word their predecessor retracted in round 0 are decoded again, one warp per image,
+        // each followed through its own successors; typically two or three tiles per request.  An image whose cascade does not
+        // end (or that holds a tile its own repair passes could not verify) goes to the retry rounds from there.
+        {
+            constexpr unsigned kCascadeBudget = 192;
+            const unsigned gw = blockIdx.x * kWtWarps + (threadIdx.x >> 5), nw = gridDim.x * kWtWarps;
+            for (unsigned img = gw; img < P.n_images; img += nw) {
+                DecResult* res = P.results + img;
+                unsigned       first = 0, ntiles = P.n_tiles;
+                const uint8_t* stream = P.qoi + P.single[0];
+                uint64_t       size   = P.single[1] - P.single[0];
+                if (P.tile_first) {
+                    first = P.tile_first[img], ntiles = P.tile_first[img + 1] - first;
+                    stream = P.qoi + P.offsets[2u * img], size = P.offsets[2u * img + 1u] - P.offsets[2u * img];
+                }
+                const unsigned nreq = res->n_req;
+                unsigned       fail = kNoRedo;  // first tile the retry rounds have to start from
+                if (nreq) {
+                    const unsigned n = min(nreq, (unsigned)kCascadeReqs);
+                    if (res->first_bad[0] || nreq > (unsigned)kCascadeReqs) {  // the rounds run anyway: from the earliest tile anybody named
+                        for (unsigned i = 0; i < n; ++i) fail = min(fail, res->req[i][0]);
+                    } else {
+                        unsigned budget = kCascadeBudget, last = 0;
+                        bool     any = false;
+                        while (fail == kNoRedo) {
+                            // the requested tiles in ascending order (a served request leaves everything up to where it ends exact);
+                            // several requests for one tile are served together
+                            unsigned u = kNoRedo;
+                            for (unsigned i = 0; i < n; ++i) {
+                                const unsigned ti = res->req[i][0];
+                                if ((!any || ti > last) && ti < u) u = ti;
+                            }
+                            if (u == kNoRedo) break;
+                            Changed c{ 0u, 0u, 0u };
+                            for (unsigned i = 0; i < n; ++i)
+                                if (res->req[i][0] == u) c.lo |= res->req[i][1], c.hi |= res->req[i][2], c.prev |= res->req[i][3];
+                            any = true, last = u;
+                            unsigned v = u;
+                            while (v != kNoRedo && v < ntiles) {
+                                if (budget-- == 0) { fail = v; break; }
+                                const unsigned nx = wt_decode_tile<kStream>(P, sm, lut, 0u, first + v, img, v, ntiles, stream, size, 0u, &c);
+                                if (nx == kCascadeFail) { fail = v; break; }
+                                if (nx != kNoRedo && (nx & kScanGaveUp)) { fail = nx & ~kScanGaveUp; break; }
+                                v = nx;
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    if (fail != kNoRedo && fail < ntiles) atomicMax(&res->first_bad[0], 0xFFFFFFFFu - fail);
+                    if (res->first_bad[0]) P.control->rounds_needed = 1;
+                }
+                __syncwarp();
+            }
+            QB_GRID_SYNC();
+        }
         for (unsigned round = 1; round <= (unsigned)kDecRounds; ++round) {
-            if (P.control->any_bad[round - 1] == 0) break;  // same value in every CTA: final since the last barrier
+            if ((round == 1 ? P.control->rounds_needed : P.control->any_bad[round - 1]) == 0) break;  // same value in every CTA: final since the last barrier
             for (;;) {
                 unsigned x = 0;
                 if (lane == 0) x = atomicAdd(&P.control->tickets[round], 1u);

@@ -703,7 +703,8 @@ extern "C"
 #ifdef QB_STATS
 extern "C" int32_t qoipp_b200_debug_stats(qoipp_b200_ctx* c, uint32_t* out4)  // development aid only
 {
-    return cuda_code(cudaMemcpy(out4, static_cast<uint8_t*>(c->results.p) + offsetof(DecControl, pad), 16, cudaMemcpyDeviceToHost));
+    out4[3] = 0;
+    return cuda_code(cudaMemcpy(out4, static_cast<uint8_t*>(c->results.p) + offsetof(DecControl, pad), 12, cudaMemcpyDeviceToHost));
 }
 #endif
 #ifdef QB_TIMING

@@ -15,5 +15,5 @@ for kind, w, h, ch in [("photo", 7680, 4320, 4), ("photo", 3840, 2160, 4), ("pho
         ctx.decode_dev(d_q, n, w, h, ch, 0, 0, False, d_out, d_out.numel(), st); torch.cuda.synchronize()
         out = (C.c_uint32 * 4)()
         lib.qoipp_b200_debug_stats(ctx._h, out)
-        print(f"{kind} {w}x{h}x{ch}: tiles {(n - 14 + 895) // 896}, path {ctx.decode_status(st)}: repaired tiles (all rounds) {out[0]}, redo because pixel/alpha or slot word changed {out[1]}, "
-              f"because prev changed {out[2]}, because a successor read a changed entry / scan gave up {out[3]}")
+        print(f"{kind} {w}x{h}x{ch}: tiles {(n - 14 + 895) // 896}, path {ctx.decode_status(st)}: repaired or cascaded tiles {out[0]}, a successor must be decoded again because a pixel/alpha, slot or prev word "
+              f"changed {out[1]}, because it read a changed table entry / had not published / the scan gave up {out[2]}")
