@@ -13,6 +13,11 @@
 #include <sstream>
 #include <vector>
 
+#if defined(__linux__)
+#include <sys/mman.h>
+#include <unistd.h>
+#endif
+
 namespace fs = std::filesystem;
 
 namespace
@@ -66,6 +71,25 @@ namespace
         t.code   = qoipp_b200_ctx_create(dev, &t.ctx);
         set.all.push_back(t);
         return set.all.back();
+    }
+
+    // A zero-filled buffer for a whole image or stream (what the reference allocates too, simple.cpp:190, 390).  For large
+    // sizes the pages are requested as transparent huge pages before they are touched: the zero fill and the copy that follows
+    // then take 2 MiB faults instead of 4 KiB ones (a 133 MB image: 32 k page faults were most of the allocation time).
+    ByteVec big_buffer(std::size_t n)
+    {
+        ByteVec v;
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+        if (n >= (8u << 20)) {
+            v.reserve(n);
+            const auto page = static_cast<std::uintptr_t>(2u << 20);
+            const auto lo   = (reinterpret_cast<std::uintptr_t>(v.data()) + page - 1) & ~(page - 1);
+            const auto hi   = (reinterpret_cast<std::uintptr_t>(v.data()) + n) & ~(page - 1);
+            if (hi > lo) (void)::madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);  // advice only: failure changes nothing
+        }
+#endif
+        v.resize(n);
+        return v;
     }
 
     // C ABI code -> qoipp::Error (the enum has no device member: CUDA failures surface as IoError)
@@ -182,7 +206,7 @@ namespace qoipp
         if (not bytes) return make_error<ByteVec>(bytes.error());
         if (in_data.size() != *bytes) return make_error<ByteVec>(Error::MismatchedDesc);
         try {
-            auto out    = ByteVec(*worst_size(desc));
+            auto out    = big_buffer(*worst_size(desc));
             auto status = encode_span(out, in_data, desc);
             if (not status) return make_error<ByteVec>(status.error());
             out.resize(status->written);
@@ -289,7 +313,7 @@ namespace qoipp
         if (not bytes) return make_error<Image>(bytes.error());
         try {
             // decode_into checks capacity against the source channel count first (ref: simple.cpp:467-471)
-            auto buf  = ByteVec(std::max(*bytes, static_cast<std::size_t>(header->width) * header->height * static_cast<std::size_t>(src)));
+            auto buf  = big_buffer(std::max(*bytes, static_cast<std::size_t>(header->width) * header->height * static_cast<std::size_t>(src)));
             auto desc = decode_into(buf, in_data, target, flip_vertically);
             if (not desc) return make_error<Image>(desc.error());
             buf.resize(*bytes);
