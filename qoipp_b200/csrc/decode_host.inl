@@ -12,6 +12,9 @@ namespace
         const size_t res_bytes = kCtrlBytes + sizeof(DecResult) * P.n_images;
         QB_CUDA(c->results.reserve(res_bytes, s));
         QB_CUDA(cudaMemsetAsync(c->results.p, 0, res_bytes, s));
+        P.req_cap = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(64, P.n_tiles / 64));  // cascade requests are rare: one in ~10^4 tiles
+        QB_CUDA(c->reqs.reserve(sizeof(CascadeReq) * P.req_cap, s));
+        P.req = static_cast<CascadeReq*>(c->reqs.p);
         QB_CUDA(c->fix.reserve((size_t)P.n_tiles * kFixWords * sizeof(uint32_t), s, true));
         // one epoch per possible round; the learned-alpha lists are tagged with the first one
         QB_CUDA(c->next_epoch((uint64_t)P.n_tiles * kDecDescWords * sizeof(uint64_t), s, kDecRounds + 1));
@@ -260,6 +263,9 @@ extern "C"
             P.desc    = static_cast<uint64_t*>(c->carry.p);
             P.fix     = static_cast<uint32_t*>(c->fix.p);
             P.init    = S.init;
+            P.req_cap = (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(64, tiles / 64));
+            QB_CUDA(c->reqs.reserve(sizeof(CascadeReq) * P.req_cap, s));
+            P.req = static_cast<CascadeReq*>(c->reqs.p);
             const unsigned want   = ((unsigned)tiles + kWtWarps - 1) / kWtWarps;
             const unsigned n_ctas = std::max(1u, std::min<unsigned>(want, (unsigned)c->dec_coresident));
             decode_wt_stream_kernel<<<n_ctas, kWtThreads, kWtSmemBytes, s>>>(P);

@@ -60,7 +60,6 @@ namespace qb
     };
 
     constexpr int kDecRounds = 4;  // verification-driven retry rounds before the sequential loop takes over
-    constexpr int kCascadeReqs = 7;  // cascade requests an image can hold; more of them send it to the retry rounds
 
     struct DecResult {
         uint32_t bad;   // round 0 refuted a speculation somewhere in this image
@@ -71,17 +70,20 @@ namespace qb
         uint32_t first_bad[kDecRounds + 1];  // per round: 0 = all verified, else 0xFFFFFFFF - first refuted tile
         uint32_t pad[3];
         DecState state;
-        // round 0 -> cascade (decode_finish_body): tiles that consumed a word their repaired predecessor retracted, each with the
-        // table entries / prev that had changed on entering it
-        uint32_t n_req, req_pad;
-        uint32_t req[kCascadeReqs][4];  // {tile, changed slots 0..31, 32..63, prev}
+    };
+
+    // round 0 -> cascade (decode_finish_body): a tile that consumed a word its repaired predecessor retracted, with the table
+    // entries / prev that had changed on entering it
+    struct CascadeReq {
+        uint32_t img, tile, lo, hi, prev, pad;
     };
 
     struct DecControl {  // zeroed with the results before every decode
         uint32_t tickets[kDecRounds + 1];  // tile tickets of round 0 and of the retry rounds
         uint32_t any_bad[kDecRounds + 1];  // some image needs round r + 1
-        uint32_t rounds_needed;            // set by the cascade (decode_finish_body): some image still needs retry round 1
-        uint32_t pad[3];
+        uint32_t rounds_needed;            // some image needs retry round 1 (a tile stayed refuted, or its cascade did not end)
+        uint32_t n_req;                    // cascade requests of round 0 (may exceed the capacity: the surplus went to the rounds)
+        uint32_t pad[2];
     };
 
     struct DecParams {
@@ -98,6 +100,8 @@ namespace qb
         DecControl*     control;
         uint64_t*       desc;
         uint32_t*       fix;  // [n_tiles][kFixWords]: alpha learned at OP_RGB ops by earlier rounds
+        CascadeReq*     req;      // [req_cap] cascade requests of round 0
+        uint32_t        req_cap;
         const DecState* init;  // resumable decode (wt_decode_tile<true>): the state the chunk stream is entered with; null otherwise
     };
 
@@ -422,7 +426,7 @@ namespace qb
     __device__ QB_NOINLINE void wt_flag_redo(const DecParams& P, unsigned round, DecResult* res, unsigned from)
     {
         if ((threadIdx.x & 31u) == 0) {
-            if (round == 0) atomicOr(&res->bad, 1u);
+            if (round == 0) atomicOr(&res->bad, 1u), P.control->rounds_needed = 1;
             atomicMax(&res->first_bad[round], 0xFFFFFFFFu - from);
             P.control->any_bad[round] = 1;
         }
@@ -435,13 +439,13 @@ namespace qb
     // after the round by the cascade of decode_finish_body: that tile alone is decoded again, then whatever read ITS changed
     // words, ... -- a handful of tiles instead of everything behind it.  `c` = what had changed on entering `from`.
     constexpr unsigned kCascadeFail = 0xFFFFFFFEu;
-    __device__ QB_NOINLINE void wt_flag_cascade(const DecParams& P, DecResult* res, unsigned from, const Changed& c)
+    __device__ QB_NOINLINE void wt_flag_cascade(const DecParams& P, DecResult* res, unsigned img, unsigned from, const Changed& c)
     {
         if ((threadIdx.x & 31u) == 0) {
             atomicOr(&res->bad, 2u);
-            const unsigned i = atomicAdd(&res->n_req, 1u);
-            if (i < (unsigned)kCascadeReqs) res->req[i][0] = from, res->req[i][1] = c.lo, res->req[i][2] = c.hi, res->req[i][3] = c.prev;
-            else atomicMax(&res->first_bad[0], 0xFFFFFFFFu - from);  // no room: everything from there on in the retry round
+            const unsigned i = atomicAdd(&P.control->n_req, 1u);
+            if (i < P.req_cap) P.req[i] = CascadeReq{ img, from, c.lo, c.hi, c.prev, 0u };
+            else atomicMax(&res->first_bad[0], 0xFFFFFFFFu - from), P.control->rounds_needed = 1;  // no room: the retry round, from there on
             P.control->any_bad[0] = 1;
         }
     }
@@ -546,7 +550,7 @@ namespace qb
             if (!ep.valid(wl, u) || !ep.valid(wh, u)) return kScanGaveUp | u;
             const uint64_t nl = word_payload(wl), nh = word_payload(wh);
             if (((unsigned)nl & dlo) | ((unsigned)nh & dhi) | dprev) {  // tile u read a changed entry (prev is always read)
-                QB_COUNT(P, 2);
+                QB_COUNT(P, 1);
                 c = Changed{ dlo, dhi, dprev };
                 return u;
             }
@@ -1122,7 +1126,7 @@ namespace qb
             const unsigned nx = wt_repair_scan(P, desc, t, ntiles, ep, old_word, dirty, c);
             if (nx != kNoRedo) {
                 if (cascade) next = nx, *casc = c;  // the caller goes on there (or gives up: kScanGaveUp)
-                else if (round == 0 && !(nx & kScanGaveUp)) wt_flag_cascade(P, res, nx, c);
+                else if (round == 0 && P.req_cap && !(nx & kScanGaveUp)) wt_flag_cascade(P, res, img, nx, c);
                 else wt_flag_redo(P, round, res, nx & ~kScanGaveUp);
             }
         }
@@ -1378,14 +1382,19 @@ namespace qb
         const unsigned lane = threadIdx.x & 31u;
         if (P.control->any_bad[0] == 0 && P.control->any_bad[kDecRounds] == 0) return;  // everything verified in round 0 (same value in every CTA)
         wt_build_lut(lut);
-        // ---- cascade: tiles that consumed a word their predecessor retracted in round 0 are decoded again, one warp per image,
-        // each followed through its own successors; typically two or three tiles per request.  An image whose cascade does not
-        // end (or that holds a tile its own repair passes could not verify) goes to the retry rounds from there.
+        // ---- cascade: a tile that consumed a word its predecessor retracted in round 0 is decoded again, then whatever read ITS
+        // changed words, ... -- typically two or three tiles per request.  One warp per image takes the image's requests in
+        // ascending tile order (a served request leaves everything up to where it ends exact; two requests of one image never
+        // run at the same time: a look-back of the later one may reach into the tiles the earlier one is rewriting).  An image
+        // whose requests need more than kCascadeBudget tile decodes, a request that finds a tile still refuted, and a scan
+        // that cannot tell send the image to the retry rounds from there.
         {
-            constexpr unsigned kCascadeBudget = 192;
+            constexpr unsigned kCascadeBudget = 48;
             const unsigned gw = blockIdx.x * kWtWarps + (threadIdx.x >> 5), nw = gridDim.x * kWtWarps;
-            for (unsigned img = gw; img < P.n_images; img += nw) {
+            const unsigned total = min(P.control->n_req, P.req_cap);
+            for (unsigned img = gw; img < P.n_images && total; img += nw) {
                 DecResult* res = P.results + img;
+                if (!(res->bad & 2u)) continue;
                 unsigned       first = 0, ntiles = P.n_tiles;
                 const uint8_t* stream = P.qoi + P.single[0];
                 uint64_t       size   = P.single[1] - P.single[0];
@@ -1393,43 +1402,38 @@ namespace qb
                     first = P.tile_first[img], ntiles = P.tile_first[img + 1] - first;
                     stream = P.qoi + P.offsets[2u * img], size = P.offsets[2u * img + 1u] - P.offsets[2u * img];
                 }
-                const unsigned nreq = res->n_req;
-                unsigned       fail = kNoRedo;  // first tile the retry rounds have to start from
-                if (nreq) {
-                    const unsigned n = min(nreq, (unsigned)kCascadeReqs);
-                    if (res->first_bad[0] || nreq > (unsigned)kCascadeReqs) {  // the rounds run anyway: from the earliest tile anybody named
-                        for (unsigned i = 0; i < n; ++i) fail = min(fail, res->req[i][0]);
-                    } else {
-                        unsigned budget = kCascadeBudget, last = 0;
-                        bool     any = false;
-                        while (fail == kNoRedo) {
-                            // the requested tiles in ascending order (a served request leaves everything up to where it ends exact);
-                            // several requests for one tile are served together
-                            unsigned u = kNoRedo;
-                            for (unsigned i = 0; i < n; ++i) {
-                                const unsigned ti = res->req[i][0];
-                                if ((!any || ti > last) && ti < u) u = ti;
-                            }
-                            if (u == kNoRedo) break;
-                            Changed c{ 0u, 0u, 0u };
-                            for (unsigned i = 0; i < n; ++i)
-                                if (res->req[i][0] == u) c.lo |= res->req[i][1], c.hi |= res->req[i][2], c.prev |= res->req[i][3];
-                            any = true, last = u;
-                            unsigned v = u;
-                            while (v != kNoRedo && v < ntiles) {
-                                if (budget-- == 0) { fail = v; break; }
-                                const unsigned nx = wt_decode_tile<kStream>(P, sm, lut, 0u, first + v, img, v, ntiles, stream, size, 0u, &c);
-                                if (nx == kCascadeFail) { fail = v; break; }
-                                if (nx != kNoRedo && (nx & kScanGaveUp)) { fail = nx & ~kScanGaveUp; break; }
-                                v = nx;
-                            }
-                        }
+                unsigned fail = kNoRedo, budget = kCascadeBudget, last = 0;
+                bool     any = false;
+                const bool rounds_anyway = res->first_bad[0] != 0;  // a tile of round 0 stayed refuted: only the earliest request matters
+                while (fail == kNoRedo) {
+                    // the smallest requested tile above the last one served, with everything that was asked for it
+                    unsigned u = kNoRedo;
+                    for (unsigned j0 = 0; j0 < total; j0 += 32u) {
+                        const unsigned j = j0 + lane;
+                        unsigned tj = kNoRedo;
+                        if (j < total && P.req[j].img == img && (!any || P.req[j].tile > last)) tj = P.req[j].tile;
+                        u = min(u, __reduce_min_sync(kFull, tj));
+                    }
+                    if (u == kNoRedo) break;
+                    if (rounds_anyway) { fail = u; break; }
+                    Changed c{ 0u, 0u, 0u };
+                    for (unsigned j0 = 0; j0 < total; j0 += 32u) {
+                        const unsigned j = j0 + lane;
+                        unsigned lo = 0, hi = 0, pv = 0;
+                        if (j < total && P.req[j].img == img && P.req[j].tile == u) lo = P.req[j].lo, hi = P.req[j].hi, pv = P.req[j].prev;
+                        c.lo |= __reduce_or_sync(kFull, lo), c.hi |= __reduce_or_sync(kFull, hi), c.prev |= __reduce_or_sync(kFull, pv);
+                    }
+                    any = true, last = u;
+                    unsigned v = u;
+                    while (v != kNoRedo && v < ntiles) {
+                        if (budget-- == 0) { fail = v; break; }
+                        const unsigned nx = wt_decode_tile<kStream>(P, sm, lut, 0u, first + v, img, v, ntiles, stream, size, 0u, &c);
+                        if (nx == kCascadeFail) { fail = v; break; }
+                        if (nx != kNoRedo && (nx & kScanGaveUp)) { fail = nx & ~kScanGaveUp; break; }
+                        v = nx;
                     }
                 }
-                if (lane == 0) {
-                    if (fail != kNoRedo && fail < ntiles) atomicMax(&res->first_bad[0], 0xFFFFFFFFu - fail);
-                    if (res->first_bad[0]) P.control->rounds_needed = 1;
-                }
+                if (lane == 0 && fail != kNoRedo && fail < ntiles) atomicMax(&res->first_bad[0], 0xFFFFFFFFu - fail), P.control->rounds_needed = 1;
                 __syncwarp();
             }
             QB_GRID_SYNC();

@@ -174,6 +174,7 @@ struct qoipp_b200_ctx {
     DevBuf   state;       // EncState / DecState carry-in for the resumable calls
     DevBuf   aux;         // decode: per-image offsets and first-tile ids of a batch
     DevBuf   fix;         // decode: per-tile lists of alphas learned by the retry rounds
+    DevBuf   reqs;        // decode: cascade requests of round 0
     DevBuf   scratch;     // encode_ts_kernel: per-tile records, read by encode_ts_copy_kernel
     DevBuf   counts;      // encode_ts_kernel: byte counts per tile and per 64-tile group
     DevBuf   stage_in, stage_out;  // device staging of the host-pointer calls
@@ -484,7 +485,7 @@ extern "C"
         if (!c) return 0;
         Guard g(c->device);
         cudaDeviceSynchronize();
-        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release(), c->scratch.release(), c->counts.release();
+        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release(), c->reqs.release(), c->scratch.release(), c->counts.release();
         c->stage_in.release(), c->stage_out.release();
         c->h_result.release(), c->h_pin_in.release(), c->h_pin_out.release(), c->ring.release();
         for (auto& e : c->ring_ev)
@@ -703,8 +704,8 @@ extern "C"
 #ifdef QB_STATS
 extern "C" int32_t qoipp_b200_debug_stats(qoipp_b200_ctx* c, uint32_t* out4)  // development aid only
 {
-    out4[3] = 0;
-    return cuda_code(cudaMemcpy(out4, static_cast<uint8_t*>(c->results.p) + offsetof(DecControl, pad), 12, cudaMemcpyDeviceToHost));
+    out4[2] = out4[3] = 0;
+    return cuda_code(cudaMemcpy(out4, static_cast<uint8_t*>(c->results.p) + offsetof(DecControl, pad), 8, cudaMemcpyDeviceToHost));
 }
 #endif
 #ifdef QB_TIMING

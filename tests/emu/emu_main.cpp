@@ -135,7 +135,8 @@ extern "C"
         DecControl             ctl;
         memset(res.data(), 0, sizeof(DecResult) * n_images);
         memset(&ctl, 0, sizeof ctl);
-        P.desc = desc.data(); P.results = res.data(); P.control = &ctl; P.fix = fix.data();
+        std::vector<CascadeReq> reqs(64);
+        P.desc = desc.data(); P.results = res.data(); P.control = &ctl; P.fix = fix.data(); P.req = reqs.data(); P.req_cap = (uint32_t)reqs.size();
         P.epoch = 5; P.round = 0;
         const unsigned n_ctas = std::max(1u, std::min<unsigned>((P.n_tiles + kWtWarps - 1) / kWtWarps, (unsigned)resident));
         if (!force_serial) {
@@ -180,10 +181,11 @@ extern "C"
         const uint64_t tiles = (in_size + kDecTB - 1) / kDecTB;
         std::vector<uint64_t> desc((size_t)tiles * kDecDescWords + 1, 0);
         std::vector<uint32_t> fix((size_t)tiles * kFixWords + 1, 0xDEADBEEFu);
+        std::vector<CascadeReq> reqs(64);
         if (parallel && tiles > 0) {
             DecParams& P = S.d;
             P.offsets = nullptr; P.tile_first = nullptr; P.n_tiles = (uint32_t)tiles; P.epoch = 7; P.round = 0;
-            P.control = &ctl; P.desc = desc.data(); P.fix = fix.data(); P.init = &is;
+            P.control = &ctl; P.desc = desc.data(); P.fix = fix.data(); P.init = &is; P.req = reqs.data(); P.req_cap = (uint32_t)reqs.size();
             const unsigned n_ctas = std::max(1u, std::min<unsigned>((P.n_tiles + kWtWarps - 1) / kWtWarps, (unsigned)resident));
             const DecParams PP = P;
             emu::launch(dim3(n_ctas), dim3(kWtThreads), kWtSmemBytes + 128, [=] { decode_wt_stream_kernel(PP); }, (int)n_ctas, seed);
