@@ -45,3 +45,15 @@ def test_qoiconv_round_trip_on_disk(tmp_path):
         assert np.array_equal(np.fromfile(tmp_path / "out.raw", dtype=np.uint8), raw)
     r = subprocess.run([tool, "info", str(tmp_path / "in.raw")], capture_output=True, text=True)
     assert r.returncode == 1 and "Not a QOI file" in r.stderr
+
+
+@pytest.mark.gpu
+def test_thread_per_gpu_example_serves_every_gpu(tmp_path):
+    """examples/batch_multi_gpu: one host thread per GPU selects its device with qoipp::b200::set_device and runs the ordinary
+    qoipp::encode / qoipp::decode; image k of B on GPU floor(k*G/B) (all GPUs of the box; one is enough for the test to mean
+    something: the example checks qoipp::b200::device() inside every call)."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "qoipp_b200", "csrc", "cxx")], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(ROOT, "examples", "batch_multi_gpu"), "24", "256", "192", "4"], capture_output=True, text=True, timeout=600)
+    print(r.stdout, r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failures" in r.stdout.splitlines()[-1]
