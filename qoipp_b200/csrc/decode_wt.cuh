@@ -40,8 +40,8 @@
 // (profiles/r02_experiments.md: 98 KB of SASS, hit rate 88 %, time proportional to the number of tiles whatever the
 // occupancy).  Helpers that are called once per tile, or are cold, are real calls instead of inlined copies.
 #define QB_NOINLINE __noinline__
-#ifdef QB_STATS  // development build: event counters in DecControl::pad (tools/stats_probe.py)
-#define QB_COUNT(P, i) do { if ((threadIdx.x & 31u) == 0) atomicAdd(&(P).control->pad[i], 1u); } while (0)
+#ifdef QB_STATS  // development build: event counters in DecControl::stats (tools/stats_probe.py)
+#define QB_COUNT(P, i) do { if ((threadIdx.x & 31u) == 0) atomicAdd(&(P).control->stats[i], 1u); } while (0)
 #else
 #define QB_COUNT(P, i) do { } while (0)
 #endif
@@ -83,7 +83,8 @@ namespace qb
         uint32_t any_bad[kDecRounds + 1];  // some image needs round r + 1
         uint32_t rounds_needed;            // some image needs retry round 1 (a tile stayed refuted, or its cascade did not end)
         uint32_t n_req;                    // cascade requests of round 0 (may exceed the capacity: the surplus went to the rounds)
-        uint32_t pad[2];
+        uint32_t list_n, list_tiles;       // work list of a retry round: images on it, tiles in their ranges
+        uint32_t stats[2];                 // development builds (QB_STATS)
     };
 
     struct DecParams {
@@ -640,12 +641,43 @@ namespace qb
             const unsigned cfull = cbeg + kWtChunk;
             const unsigned exit0 = p > cfull ? p - cfull : 0u;
             unsigned       win   = exit0;
+#ifdef QB_WT_ALL_ENTRIES
 #pragma unroll 1
             for (unsigned e = 1; e <= 4u; ++e) {  // a late entry usually falls into the path of entry 0 after an op or two
                 unsigned q = cbeg + e;
                 while (q < cend && !((M0 >> (q - cbeg)) & 1u)) q += (lut_y[2u * B[q]] >> 14) & 7u;
                 win |= (q < cend ? exit0 : (q > cfull ? q - cfull : 0u)) << (3u * e);
             }
+#else
+            // Only the entry offsets a chunk can really be entered at are walked: lane 0 can be entered anywhere (the tile's
+            // entry is not known yet), lane l only at an exit of lane l - 1 over the entries IT can be entered at -- nearly
+            // always the single exit of its path 0.  Entries that cannot occur keep a meaningless exit in the map: composition
+            // never selects them.  The sets grow until nothing new appears (two rounds as a rule; walking all four late
+            // entries of every lane was the most expensive line of the kernel, 4.8 % of its instructions).
+            unsigned have = 1u, outs = 1u << exit0;  // entries walked / exits they produced, as sets
+            auto walk_entry = [&](unsigned e) {
+                unsigned q = cbeg + e;
+                while (q < cend && !((M0 >> (q - cbeg)) & 1u)) q += (lut_y[2u * B[q]] >> 14) & 7u;
+                const unsigned ex = q < cend ? exit0 : (q > cfull ? q - cfull : 0u);
+                win |= ex << (3u * e), have |= 1u << e, outs |= 1u << ex;
+            };
+            if (lane == 0) {
+#pragma unroll 1
+                for (unsigned e = 1; e <= 4u; ++e) walk_entry(e);
+            }
+            for (;;) {
+                unsigned need = __shfl_up_sync(kFull, outs, 1);
+                if (lane == 0) need = 0;
+                need &= ~have;
+                if (__ballot_sync(kFull, need != 0) == 0) break;
+#pragma unroll 1
+                while (need) {
+                    const unsigned e = (unsigned)__ffs((int)need) - 1u;
+                    need &= need - 1u;
+                    walk_entry(e);
+                }
+            }
+#endif
             mymap = map_unpack(win);
         }
         Map incl_map = mymap;
@@ -1440,18 +1472,72 @@ namespace qb
         }
         for (unsigned round = 1; round <= (unsigned)kDecRounds; ++round) {
             if ((round == 1 ? P.control->rounds_needed : P.control->any_bad[round - 1]) == 0) break;  // same value in every CTA: final since the last barrier
+            // Work list of the round: the images that need it, each with the range of tiles from its first affected one on, in
+            // the (dead by now) request array; tickets run over the concatenated ranges.  (One ticket and one image search per
+            // tile of the whole batch -- 4.5 M tiles for 8192 images, a handful of them with work -- cost 12 ms.)
+            const unsigned gw = blockIdx.x * kWtWarps + (threadIdx.x >> 5), nw = gridDim.x * kWtWarps;
+            uint32_t*      nlist = &P.control->list_n;  // entries in the list; reset below for the next round
+            bool           listed = P.n_images > 1 && P.req_cap >= 2;
+            if (listed) {
+                for (unsigned img = gw * 32u + lane; img < P.n_images; img += nw * 32u) {
+                    const unsigned fb = P.results[img].first_bad[round - 1];
+                    if (fb) {
+                        const unsigned from = 0xFFFFFFFFu - fb, i = atomicAdd(nlist, 1u);
+                        if (i < P.req_cap) P.req[i] = CascadeReq{ img, from, P.tile_first[img + 1] - P.tile_first[img] - from, 0u, 0u, 0u };
+                    }
+                }
+                QB_GRID_SYNC();
+                const unsigned K = *nlist;
+                listed = K <= P.req_cap;  // else: the full loop below
+                if (listed && gw == 0) {  // exclusive prefix of the range lengths -> .hi
+                    unsigned run = 0;
+                    for (unsigned j0 = 0; j0 < K; j0 += 32u) {
+                        const unsigned j = j0 + lane, n = j < K ? P.req[j].lo : 0u;
+                        unsigned inc = n;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const unsigned o = __shfl_up_sync(kFull, inc, d);
+                            if ((int)lane >= d) inc += o;
+                        }
+                        if (j < K) P.req[j].hi = run + inc - n;
+                        run += __shfl_sync(kFull, inc, 31);
+                    }
+                    if (lane == 0) P.control->list_tiles = run;
+                }
+                QB_GRID_SYNC();
+            }
+            const unsigned K = listed ? *nlist : 0u, W = listed ? P.control->list_tiles : P.n_tiles;
             for (;;) {
                 unsigned x = 0;
                 if (lane == 0) x = atomicAdd(&P.control->tickets[round], 1u);
                 x = __shfl_sync(kFull, x, 0);
-                if (x >= P.n_tiles) break;
-                unsigned       img, t, ntiles;
+                if (x >= W) break;
+                unsigned       img, t, ntiles, gt;
                 const uint8_t* stream;
                 uint64_t       size;
-                locate_image(P, x, img, t, ntiles, stream, size);
+                if (listed) {
+                    unsigned lo = 0, hi = K;  // the range that holds ticket x
+                    while (hi - lo > 1) {
+                        const unsigned mid = (lo + hi) >> 1;
+                        if (P.req[mid].hi <= x) lo = mid;
+                        else hi = mid;
+                    }
+                    img = P.req[lo].img, t = P.req[lo].tile + (x - P.req[lo].hi);
+                    const unsigned f = P.tile_first[img];
+                    gt = f + t, ntiles = P.tile_first[img + 1] - f;
+                    const uint64_t o0 = P.offsets[2u * img];
+                    stream = P.qoi + o0, size = P.offsets[2u * img + 1u] - o0;
+                } else {
+                    gt = x;
+                    locate_image(P, x, img, t, ntiles, stream, size);
+                }
                 const unsigned fb = P.results[img].first_bad[round - 1];
                 if (fb == 0 || t < 0xFFFFFFFFu - fb) continue;  // image verified, or a tile before the first refuted one: final
-                wt_decode_tile<kStream>(P, sm, lut, round, x, img, t, ntiles, stream, size, 0xFFFFFFFFu - fb);
+                wt_decode_tile<kStream>(P, sm, lut, round, gt, img, t, ntiles, stream, size, 0xFFFFFFFFu - fb);
+            }
+            if (listed) {
+                QB_GRID_SYNC();
+                if (gw == 0 && lane == 0) *nlist = 0;
             }
             QB_GRID_SYNC();
         }

@@ -705,7 +705,7 @@ extern "C"
 extern "C" int32_t qoipp_b200_debug_stats(qoipp_b200_ctx* c, uint32_t* out4)  // development aid only
 {
     out4[2] = out4[3] = 0;
-    return cuda_code(cudaMemcpy(out4, static_cast<uint8_t*>(c->results.p) + offsetof(DecControl, pad), 8, cudaMemcpyDeviceToHost));
+    return cuda_code(cudaMemcpy(out4, static_cast<uint8_t*>(c->results.p) + offsetof(DecControl, stats), 8, cudaMemcpyDeviceToHost));
 }
 #endif
 #ifdef QB_TIMING
