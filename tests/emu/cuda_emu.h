@@ -56,7 +56,30 @@ namespace emu
         bool     done = false;
         Wait     wait = Wait::None;
         uint64_t wait_gen = 0;
+        // the stack belongs to the fiber: a CTA taken from the pool for a smaller block gives the surplus back
+        // (kernels of 256 and of 32 threads alternate in the resumable decode: 224 leaked stacks per call otherwise)
+        Fiber() = default;
+        Fiber(const Fiber&) = delete;
+        Fiber& operator=(const Fiber&) = delete;
+        Fiber(Fiber&& o) noexcept : sp(o.sp), stack(o.stack), cta(o.cta), tid(o.tid), done(o.done), wait(o.wait), wait_gen(o.wait_gen) { o.stack = nullptr; }
+        Fiber& operator=(Fiber&& o) noexcept
+        {
+            if (this != &o) {
+                release();
+                sp = o.sp, stack = o.stack, cta = o.cta, tid = o.tid, done = o.done, wait = o.wait, wait_gen = o.wait_gen;
+                o.stack = nullptr;
+            }
+            return *this;
+        }
+        ~Fiber() { release(); }
+        inline void release();
     };
+
+    inline void Fiber::release()
+    {
+        if (stack) munmap(stack, kStack);
+        stack = nullptr;
+    }
 
     struct WarpRv {  // rendezvous state of one warp
         uint32_t arrived = 0, mask = 0;
