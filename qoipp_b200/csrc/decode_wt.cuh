@@ -130,14 +130,14 @@ namespace qb
     constexpr unsigned kSlRgb = 0x40u, kSlIdx = 0x80u;  // flags beside the 6-bit slot
 
 #ifdef QB_TIMING
-    constexpr int kDecDescWords = 80;  // development build: words 72..79 hold phase stamps (tools/phase_probe_wt.py)
+    constexpr int kDecDescWords = 80;  // development build: words 72..79 hold phase stamps (tools/phase_probe_wt.py), no top-level totals
 #else
-    constexpr int kDecDescWords = 72;
+    constexpr int kDecDescWords = 73;
 #endif
     constexpr int kDwParse = 0, kDwPixA = 1, kDwSlot = 2, kDwState = 3;  // 3..67: 64 table entries, then prev
     constexpr int kDwNeedLo = 70, kDwNeedHi = 71;  // entries of the incoming state this tile read (slots 0..31 / 32..63, bit 32: prev)
-    constexpr int kDwGrp = 68, kDwSup = 69;  // totals of the 64 tiles / 4096 tiles ending with this tile (see wt_gather_pixa)
-    constexpr unsigned kGrp = 64, kSup = 4096;
+    constexpr int kDwGrp = 68, kDwSup = 69, kDwTop = 72;  // totals of the 32 / 1024 / 32768 tiles ending with this tile (see wt_gather_pixa)
+        constexpr unsigned kGrp = 32, kSup = 32 * kGrp, kTop = 32 * kSup;  // every level folds <= 31 words: one warp step
     constexpr int kFixWords = 16, kFixMax = kFixWords - 1;  // word 0: count | decode tag << 8; entries: pos | alpha << 16
 
     // parse map of a byte range: exit offset for each of the five possible entry offsets.  Entries 0..3 live in the
@@ -265,7 +265,7 @@ namespace qb
 
     // ---- pixels before tile t of its image and the alpha of the last OP_RGBA before it, WITHOUT a chain: every tile
     // publishes its own count (kDwPixA) right after its parse; the last tile of every 64 (4096) sums its group
-    // (super-group) from those words (kDwGrp / kDwSup, in its own descriptor).  A reader folds <= 63 tile words, <= 63
+    // (super-group, top-level group) from those words (kDwGrp / kDwSup / kDwTop, in its own descriptor).  A reader folds <= 31 tile words, <= 31
     // group words and the super-group words before it: it waits for tiles that started before it to pass their parse,
     // never for a predecessor's own prefix.  (A chained look-back of this sum moved at 32 tiles per L2 round trip: the
     // whole decode was bounded by it, profiles/r02_experiments.md.)  All lanes of one warp call this together.
@@ -302,8 +302,16 @@ namespace qb
         // stay one after the other.)
         PixA           acc{ 0u, 0u, 0x1FFu };  // before the stream: no pixels, alpha 255
         if (init) acc = PixA{ init->run, 0u, 0x100u | (init->prev >> 24) };  // resumable decode: the pending run comes first (stream.cpp:335-339)
-        const unsigned s = t / kSup, g = t / kGrp, r = t % kGrp;
-        for (unsigned j = 0; j < s; j += 64u)  // super-groups before mine
+        const unsigned top = t / kTop, s = t / kSup, g = t / kGrp, r = t % kGrp;
+#ifndef QB_TIMING
+        for (unsigned j = 0; j < top; j += 64u)  // top-level groups before mine (one per 32768 tiles: 29 MB of stream)
+            acc = pixa_comb(acc, wt_fold_words(d_t, t, j * kTop + kTop - 1u, min(64u, top - j), kTop, kDwTop, ep));
+        const unsigned s0 = top * (kTop / kSup);  // super-groups of my top-level group before mine
+#else
+        const unsigned s0 = 0;
+        (void)top;
+#endif
+        for (unsigned j = s0; j < s; j += 64u)
             acc = pixa_comb(acc, wt_fold_words(d_t, t, j * kSup + kSup - 1u, min(64u, s - j), kSup, kDwSup, ep));
         const unsigned g0 = s * (kSup / kGrp);  // groups of my super-group before mine
         if (g > g0) acc = pixa_comb(acc, wt_fold_words(d_t, t, g0 * kGrp + kGrp - 1u, g - g0, kGrp, kDwGrp, ep));
@@ -320,6 +328,11 @@ namespace qb
         if (t % kSup != kSup - 1u) return;
         const PixA sup = pixa_comb(wt_fold_words(d_t, t, t - (kSup - kGrp), kSup / kGrp - 1u, kGrp, kDwGrp, ep), grp);
         if (lane == 0) st_word(d_t + kDwSup, pack_word(pixa_pack(sup), ST_INCL, epoch));
+#ifndef QB_TIMING
+        if (t % kTop != kTop - 1u) return;
+        const PixA tp = pixa_comb(wt_fold_words(d_t, t, t - (kTop - kSup), kTop / kSup - 1u, kSup, kDwSup, ep), sup);
+        if (lane == 0) st_word(d_t + kDwTop, pack_word(pixa_pack(tp), ST_INCL, epoch));
+#endif
     }
 
     // incoming value of state entry `e` (0..63 table slot, 64 prev) of tile `t`: follow the chain of transfer words
