@@ -52,7 +52,9 @@ namespace qb
         uint32_t*       ticket;
         uint32_t*       scratch;     // encode_ts_kernel: per-tile records, read by encode_ts_copy_kernel
         uint32_t*       tile_bytes;  // encode_ts_kernel: [tiles] byte count of every tile
-        uint32_t*       group_bytes; // encode_ts_kernel: [n_images][groups_per_image] totals of 64-tile groups (zeroed before launch)
+        uint32_t*       group_bytes; // encode_ts_kernel: [n_images][groups_per_image] totals of 64-tile groups (zero at launch)
+        uint32_t*       zero_ptr;    // encode_ts_copy_kernel clears these zero_n words: the group totals of the PREVIOUS encode, which the
+        uint32_t        zero_n;      // next one will use (two buffers take turns, so no memset is launched between encodes)
         uint32_t        groups_per_image;
         uint32_t        ticket_base[1];  // encode_ts_kernel: value of *ticket at launch (never reset)
     };

@@ -488,6 +488,7 @@ namespace qb
     {
         TsCopySmem&    sm = reinterpret_cast<TsCopySmem*>(QB_DYN_SMEM)[threadIdx.x >> 5];
         const unsigned gt = blockIdx.x * kTsCopyWarps + (threadIdx.x >> 5);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < P.zero_n; i += gridDim.x * blockDim.x) P.zero_ptr[i] = 0;
         if (gt < P.tiles_per_image * P.n_images) ts_copy_tile<CH>(P, sm, gt);
     }
 }  // namespace qb

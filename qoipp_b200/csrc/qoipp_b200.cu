@@ -176,7 +176,10 @@ struct qoipp_b200_ctx {
     DevBuf   fix;         // decode: per-tile lists of alphas learned by the retry rounds
     DevBuf   reqs;        // decode: cascade requests of round 0
     DevBuf   scratch;     // encode_ts_kernel: per-tile records, read by encode_ts_copy_kernel
-    DevBuf   counts;      // encode_ts_kernel: byte counts per tile and per 64-tile group
+    DevBuf   counts;      // encode_ts_kernel: byte counts per tile
+    DevBuf   groups[2];   // encode_ts_kernel: totals per 64-tile group; the two take turns, each cleared by the other's copy kernel
+    size_t   groups_dirty[2] = { 0, 0 };  // leading words of groups[i] that are not known to be zero
+    int      groups_cur = 0;
     DevBuf   stage_in, stage_out;  // device staging of the host-pointer calls
     PinnedBuf h_result;   // pinned landing zone for result structs
     PinnedBuf h_pin_in, h_pin_out;
@@ -297,12 +300,28 @@ namespace
             const uint64_t scr_words = ch == 3 ? TsCfg<3>::kScrWords : TsCfg<4>::kScrWords;
             const uint64_t groups    = (tiles + 63) / 64;
             QB_CUDA(c->scratch.reserve(n_tiles * scr_words * 4, s));
-            QB_CUDA(c->counts.reserve((n_tiles + groups * n_images) * 4, s));
+            QB_CUDA(c->counts.reserve(n_tiles * 4, s));
             P.scratch          = static_cast<uint32_t*>(c->scratch.p);
             P.tile_bytes       = static_cast<uint32_t*>(c->counts.p);
-            P.group_bytes      = P.tile_bytes + n_tiles;
             P.groups_per_image = (uint32_t)groups;
-            QB_CUDA(cudaMemsetAsync(P.group_bytes, 0, groups * n_images * 4, s));
+            // group totals: this encode adds into one buffer (zero by now) and its copy kernel clears what the previous encode
+            // left in the other, so that no memset sits between two encodes
+            {
+                const int    cur = c->groups_cur, oth = cur ^ 1;
+                const size_t need = groups * n_images;
+                if (need * 4 > c->groups[cur].cap) {
+                    QB_CUDA(c->groups[cur].reserve(need * 4, s, true));  // new memory arrives cleared
+                    c->groups_dirty[cur] = 0;
+                }
+                if (c->groups_dirty[cur]) {  // first use after a call that could not be followed by a copy kernel
+                    QB_CUDA(cudaMemsetAsync(c->groups[cur].p, 0, c->groups_dirty[cur] * 4, s));
+                    c->groups_dirty[cur] = 0;
+                }
+                P.group_bytes = static_cast<uint32_t*>(c->groups[cur].p);
+                P.zero_ptr    = static_cast<uint32_t*>(c->groups[oth].p);
+                P.zero_n      = (uint32_t)c->groups_dirty[oth];
+                c->groups_dirty[oth] = 0, c->groups_dirty[cur] = need, c->groups_cur = oth;
+            }
             // persistent warps: one CTA per resident slot; the ticket counter is never reset, every warp draws exactly one
             // ticket beyond the last tile
             const unsigned n_ctas = (unsigned)std::min<uint64_t>((n_tiles + kTsWarps - 1) / kTsWarps, (uint64_t)c->sm_count * QB_TS_CTAS);
@@ -325,6 +344,7 @@ namespace
             // the host-side shadow of the ticket counter was advanced for a launch that did not happen: start both from zero again
             (void)cudaMemsetAsync(c->tickets.p, 0, 64, s);
             c->ts_ticket = 0;
+            for (int i = 0; i < 2; ++i) c->groups_dirty[i] = c->groups[i].cap / 4;  // neither buffer of group totals is known to be clear
             return cuda_code(le);
         }
         return 0;
@@ -485,7 +505,7 @@ extern "C"
         if (!c) return 0;
         Guard g(c->device);
         cudaDeviceSynchronize();
-        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release(), c->reqs.release(), c->scratch.release(), c->counts.release();
+        c->carry.release(), c->tickets.release(), c->results.release(), c->state.release(), c->aux.release(), c->fix.release(), c->reqs.release(), c->scratch.release(), c->counts.release(), c->groups[0].release(), c->groups[1].release();
         c->stage_in.release(), c->stage_out.release();
         c->h_result.release(), c->h_pin_in.release(), c->h_pin_out.release(), c->ring.release();
         for (auto& e : c->ring_ev)
