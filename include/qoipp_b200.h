@@ -88,6 +88,17 @@ int32_t qoipp_b200_encode_status(qoipp_b200_ctx* ctx, void* stream, uint64_t* wr
 int32_t qoipp_b200_encode_host(qoipp_b200_ctx* ctx, const uint8_t* h_raw, uint64_t raw_size, const qoipp_b200_desc* desc,
                                uint8_t* h_out, uint64_t out_cap, uint64_t* written, int32_t* complete);
 
+/* ---- staged forms for callers that allocate their result (qoipp::encode(ByteCSpan, Desc), source/simple.cpp:178-205, and
+ * qoipp::decode(ByteCSpan, target, flip), :365-414): the result stays in the context's device staging buffer until
+ * qoipp_b200_fetch_staged copies its first n bytes to h_out.  encode_staged returns the exact size, so the caller allocates
+ * `written` bytes instead of worst_size; decode_staged returns as soon as the work is enqueued, so the caller's allocation of
+ * the image overlaps the transfer and the kernels. */
+int32_t qoipp_b200_encode_staged(qoipp_b200_ctx* ctx, const uint8_t* h_raw, uint64_t raw_size, const qoipp_b200_desc* desc,
+                                 uint64_t* written);
+int32_t qoipp_b200_decode_staged(qoipp_b200_ctx* ctx, const uint8_t* h_qoi, uint64_t qoi_size, uint8_t target_channels,
+                                 int32_t flip_vertically, qoipp_b200_desc* desc, uint64_t* out_bytes);
+int32_t qoipp_b200_fetch_staged(qoipp_b200_ctx* ctx, uint8_t* h_out, uint64_t n);
+
 /* ---- batch encode (extension): n_images equally shaped images, image k at d_raw + k*raw_stride,
  * output k at d_out + k*out_stride with capacity out_cap each; d_written[k] / d_complete[k] are device arrays
  * filled by the kernels (either may be NULL). */

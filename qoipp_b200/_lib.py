@@ -53,6 +53,9 @@ def _load():
         "qoipp_b200_encode_dev": (C.c_int32, [vp, vp, dp, vp, C.c_uint64, vp]),
         "qoipp_b200_encode_status": (C.c_int32, [vp, vp, u64p, i32p]),
         "qoipp_b200_encode_host": (C.c_int32, [vp, vp, C.c_uint64, dp, vp, C.c_uint64, u64p, i32p]),
+        "qoipp_b200_encode_staged": (C.c_int32, [vp, vp, C.c_uint64, dp, u64p]),
+        "qoipp_b200_decode_staged": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint8, C.c_int32, dp, u64p]),
+        "qoipp_b200_fetch_staged": (C.c_int32, [vp, vp, C.c_uint64]),
         "qoipp_b200_encode_batch_dev": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, dp, vp, C.c_uint64, C.c_uint64, vp, vp]),
         "qoipp_b200_encode_batch_host": (C.c_int32, [vp, vp, C.c_uint64, C.c_uint32, dp, vp, C.c_uint64, C.c_uint64, u64p]),
         "qoipp_b200_decode_batch_strided_dev": (C.c_int32, [vp, vp, C.c_uint64, u64p, C.c_uint32, dp, C.c_uint8, vp, C.c_uint64, vp]),

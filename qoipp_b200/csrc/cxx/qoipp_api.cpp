@@ -206,10 +206,15 @@ namespace qoipp
         if (not bytes) return make_error<ByteVec>(bytes.error());
         if (in_data.size() != *bytes) return make_error<ByteVec>(Error::MismatchedDesc);
         try {
-            auto out    = big_buffer(*worst_size(desc));
-            auto status = encode_span(out, in_data, desc);
-            if (not status) return make_error<ByteVec>(status.error());
-            out.resize(status->written);
+            // the stream stays on the device until its size is known: the result is allocated at that size, not at
+            // worst_size (the reference allocates and zero-fills the worst case, then shrinks: simple.cpp:190-204)
+            auto& t = thread_ctx();
+            if (not t.ctx) return make_error<ByteVec>(to_error(t.code));
+            const auto cd      = to_c(desc);
+            uint64_t   written = 0;
+            if (const auto code = qoipp_b200_encode_staged(t.ctx, in_data.data(), in_data.size(), &cd, &written)) return make_error<ByteVec>(to_error(code));
+            auto out = big_buffer(written);
+            if (const auto code = qoipp_b200_fetch_staged(t.ctx, out.data(), written)) return make_error<ByteVec>(to_error(code));
             return out;
         } catch (const std::bad_alloc&) {
             return make_error<ByteVec>(Error::BadAlloc);
@@ -312,12 +317,17 @@ namespace qoipp
         const auto bytes = count_bytes(*header);
         if (not bytes) return make_error<Image>(bytes.error());
         try {
-            // decode_into checks capacity against the source channel count first (ref: simple.cpp:467-471)
-            auto buf  = big_buffer(std::max(*bytes, static_cast<std::size_t>(header->width) * header->height * static_cast<std::size_t>(src)));
-            auto desc = decode_into(buf, in_data, target, flip_vertically);
-            if (not desc) return make_error<Image>(desc.error());
-            buf.resize(*bytes);
-            return Image{ std::move(buf), *desc };
+            // transfer and kernels are enqueued first; the image is allocated while they run, then fetched
+            auto& t = thread_ctx();
+            if (not t.ctx) return make_error<Image>(to_error(t.code));
+            qoipp_b200_desc cd{};
+            uint64_t        need = 0;
+            if (const auto code = qoipp_b200_decode_staged(t.ctx, in_data.data(), in_data.size(), target_byte(target), flip_vertically, &cd, &need))
+                return make_error<Image>(to_error(code));
+            auto buf = big_buffer(*bytes);
+            if (need != *bytes) return make_error<Image>(Error::IoError);
+            if (const auto code = qoipp_b200_fetch_staged(t.ctx, buf.data(), need)) return make_error<Image>(to_error(code));
+            return Image{ std::move(buf), from_c(cd) };
         } catch (const std::bad_alloc&) {
             return make_error<Image>(Error::BadAlloc);
         }

@@ -175,6 +175,32 @@ extern "C"
         return 0;
     }
 
+    // decode into the context's staging buffer; returns once the work is enqueued (the caller allocates meanwhile)
+    int32_t qoipp_b200_decode_staged(qoipp_b200_ctx* c, const uint8_t* h_qoi, uint64_t qoi_size, uint8_t target, int32_t flip,
+                                     qoipp_b200_desc* desc, uint64_t* out_bytes)
+    {
+        if (qoi_size == 0) return H::Empty;  // check order of qoipp::decode, source/simple.cpp:367-395
+        if (qoi_size <= H::kHeaderSize + H::kMarkerSize) return H::TooShort;
+        if (int32_t e = H::read_header(h_qoi, qoi_size, desc)) return e;
+        uint64_t src_bytes;
+        if (int32_t e = H::count_bytes(*desc, &src_bytes)) return e;
+        const unsigned tgt  = target ? target : desc->channels;
+        const uint64_t need = (uint64_t)desc->width * desc->height * tgt;
+        Guard          g(c->device);
+        cudaStream_t   s    = c->own_stream;
+        const uint8_t* d_in = mapped_host(h_qoi);
+        if (!d_in) {
+            QB_CUDA(c->stage_in.reserve(qoi_size + 64, s));
+            QB_CUDA(pageable_to_device(c, c->stage_in.p, h_qoi, qoi_size, s));
+            d_in = static_cast<uint8_t*>(c->stage_in.p);
+        }
+        QB_CUDA(c->stage_out.reserve(need + 64, s));
+        if (int32_t e = qoipp_b200_decode_dev(c, d_in, qoi_size, desc, (uint8_t)tgt, flip, static_cast<uint8_t*>(c->stage_out.p), need, s)) return e;
+        desc->channels  = (uint8_t)tgt;
+        c->staged_bytes = need, *out_bytes = need;
+        return 0;
+    }
+
     int32_t qoipp_b200_decode_batch_dev(qoipp_b200_ctx* c, const uint8_t* d_qoi, const uint64_t* h_offsets, uint32_t n_images,
                                         const qoipp_b200_desc* desc, uint8_t target, uint8_t* d_out, uint64_t out_stride,
                                         void* stream)

@@ -184,6 +184,7 @@ struct qoipp_b200_ctx {
     PinnedBuf h_result;   // pinned landing zone for result structs
     PinnedBuf h_pin_in, h_pin_out;
     std::vector<uint64_t> batch_table;      // decode_batch_dev: the offset / first-tile table of this call (host)
+    uint64_t staged_bytes = 0;  // valid bytes of stage_out left by the last *_staged call
     cudaStream_t batch_table_stream = nullptr;  // the stream that upload was ordered on
     size_t   batch_table_dev_bytes = 0;     // bytes of the table `aux` holds (a copy of it stays in h_pin_in), 0 = none
     PinnedBuf ring;              // page-locked ring of the pageable staging pipeline (2 slots)
@@ -581,6 +582,44 @@ extern "C"
         if (int32_t e = encode_one(c, d_in, desc, d_out, cap, s, !in_place)) return e;
         if (int32_t e = qoipp_b200_encode_status(c, s, written, complete)) return e;
         if (staged_out && *written) QB_CUDA(device_to_pageable(c, h_out, c->stage_out.p, *written, s));
+        return 0;
+    }
+
+    // ---- staged forms for callers that allocate their result (qoipp::encode / qoipp::decode): the output stays in the
+    // context's device staging buffer until its size is known / while the caller allocates, then _fetch_staged brings it over
+    int32_t qoipp_b200_encode_staged(qoipp_b200_ctx* c, const uint8_t* h_raw, uint64_t raw_size, const qoipp_b200_desc* desc, uint64_t* written)
+    {
+        if (raw_size == 0) return H::Empty;  // validation order of qoipp::encode, source/simple.cpp:182-188
+        uint64_t need, worst;
+        if (int32_t e = H::count_bytes(*desc, &need)) return e;
+        if (raw_size != need) return H::MismatchedDesc;
+        if (int32_t e = H::worst_size(*desc, &worst)) return e;
+        Guard          g(c->device);
+        cudaStream_t   s    = c->own_stream;
+        const uint8_t* d_in = mapped_host(h_raw);
+        if (!d_in) {
+            QB_CUDA(c->stage_in.reserve(raw_size + 16, s));
+            QB_CUDA(pageable_to_device(c, c->stage_in.p, h_raw, raw_size, s));
+            d_in = static_cast<uint8_t*>(c->stage_in.p);
+        }
+        QB_CUDA(c->stage_out.reserve(worst + 16, s));
+        if (int32_t e = encode_one(c, d_in, desc, static_cast<uint8_t*>(c->stage_out.p), worst, s, mapped_host(h_raw) == nullptr)) return e;
+        int32_t complete = 0;
+        if (int32_t e = qoipp_b200_encode_status(c, s, written, &complete)) return e;
+        c->staged_bytes = *written;
+        return 0;
+    }
+
+    int32_t qoipp_b200_fetch_staged(qoipp_b200_ctx* c, uint8_t* h_out, uint64_t n)
+    {
+        if (n > c->staged_bytes) return H::NotEnoughSpace;
+        Guard        g(c->device);
+        cudaStream_t s = c->own_stream;
+        if (n == 0) {
+            QB_CUDA(cudaStreamSynchronize(s));
+            return 0;
+        }
+        QB_CUDA(device_to_pageable(c, h_out, c->stage_out.p, n, s));
         return 0;
     }
 
