@@ -245,6 +245,9 @@ namespace
         if ((e = dec_set_attrs()) != cudaSuccess) return e;
         int per_sm = 0;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_finish_kernel, kWtThreads, kWtSmemBytes)) != cudaSuccess) return e;
+        int per_sm_stream = 0;  // both cooperative kernels are launched with the same grid: it must be co-resident for either
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_stream, decode_finish_stream_kernel, kWtThreads, kWtSmemBytes)) != cudaSuccess) return e;
+        per_sm = std::min(per_sm, per_sm_stream);
         if (const char* g = std::getenv("QOIPP_B200_DEC_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(g)));  // A/B measurements
         c->dec_coresident = std::max(1, per_sm) * c->sm_count;
         c->attrs_set = true;
