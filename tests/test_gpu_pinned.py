@@ -162,3 +162,40 @@ def test_batch_host_entry_points(ctx):
         assert np.array_equal(a_out, np.concatenate(raws))
         paths = ctx.decode_status_batch(B, 0)
         assert paths.shape == (B,) and (paths < 100).all()
+
+
+def test_staged_entry_points(ctx):
+    """qoipp_b200_encode_staged / _decode_staged / _fetch_staged (what qoipp::encode / qoipp::decode of the C++ layer call):
+    the result stays on the device until its size is known / while the caller allocates; error order of the reference."""
+    from qoipp_b200._lib import Desc, lib
+
+    for kind, w, h, ch in (("photo", 800, 450, 4), ("noise", 333, 111, 3), ("flat", 1, 1, 4)):
+        raw = synth.generate(kind, w, h, ch)
+        ref = Oracle.encode(raw, w, h, ch)
+        written = C.c_uint64(0)
+        e = lib.qoipp_b200_encode_staged(ctx._h, C.c_void_p(raw.ctypes.data), raw.size, C.byref(Desc(w, h, ch, 0)), C.byref(written))
+        assert e == 0 and written.value == ref.size
+        out = np.full(ref.size + 32, 0xAA, np.uint8)
+        assert lib.qoipp_b200_fetch_staged(ctx._h, C.c_void_p(out.ctypes.data), ref.size + 1) == 7  # more than is staged: NotEnoughSpace
+        assert lib.qoipp_b200_fetch_staged(ctx._h, C.c_void_p(out.ctypes.data), ref.size) == 0
+        assert np.array_equal(out[: ref.size], ref) and (out[ref.size:] == 0xAA).all()
+        for target, flip in ((0, False), (7 - ch, True)):
+            d, need = Desc(), C.c_uint64(0)
+            e = lib.qoipp_b200_decode_staged(ctx._h, C.c_void_p(ref.ctypes.data), ref.size, target, int(flip), C.byref(d), C.byref(need))
+            want = Oracle.decode(ref, target, flip)
+            assert e == 0 and need.value == want.size and d.channels == (target or ch)
+            px = np.full(want.size + 32, 0xAA, np.uint8)
+            assert lib.qoipp_b200_fetch_staged(ctx._h, C.c_void_p(px.ctypes.data), want.size) == 0
+            assert np.array_equal(px[: want.size], want) and (px[want.size:] == 0xAA).all()
+    raw = synth.generate("photo", 16, 16, 3)
+    wr = C.c_uint64(0)
+    assert lib.qoipp_b200_encode_staged(ctx._h, C.c_void_p(raw.ctypes.data), 0, C.byref(Desc(16, 16, 3, 0)), C.byref(wr)) == 1          # Empty
+    assert lib.qoipp_b200_encode_staged(ctx._h, C.c_void_p(raw.ctypes.data), raw.size, C.byref(Desc(16, 16, 5, 0)), C.byref(wr)) == 5  # InvalidDesc
+    assert lib.qoipp_b200_encode_staged(ctx._h, C.c_void_p(raw.ctypes.data), raw.size - 3, C.byref(Desc(16, 16, 3, 0)), C.byref(wr)) == 6  # MismatchedDesc
+    q = Oracle.encode(raw, 16, 16, 3)
+    d, need = Desc(), C.c_uint64(0)
+    assert lib.qoipp_b200_decode_staged(ctx._h, C.c_void_p(q.ctypes.data), 0, 0, 0, C.byref(d), C.byref(need)) == 1    # Empty
+    assert lib.qoipp_b200_decode_staged(ctx._h, C.c_void_p(q.ctypes.data), 22, 0, 0, C.byref(d), C.byref(need)) == 2   # TooShort
+    bad = q.copy()
+    bad[0] = ord("x")
+    assert lib.qoipp_b200_decode_staged(ctx._h, C.c_void_p(bad.ctypes.data), bad.size, 0, 0, C.byref(d), C.byref(need)) == 4  # NotQoi
