@@ -2,7 +2,9 @@
 // (image k of B goes to GPU floor(k * G / B); nothing is exchanged between GPUs).
 // Every thread selects its GPU with qoipp::b200::set_device and then uses the ordinary qoipp::encode / qoipp::decode.
 //
-//   batch_multi_gpu [images=64] [width=512] [height=512] [channels=4] [gpus=all]
+//   batch_multi_gpu [images=64] [width=512] [height=512] [channels=4] [gpus=all] [threads_per_gpu=1]
+// With threads_per_gpu > 1 several host threads drive the same GPU at once, each through its own context (the reference's
+// free functions are re-entrant; so are these).
 #include "qoipp/qoipp.hpp"
 
 #include <chrono>
@@ -28,7 +30,8 @@ int main(int argc, char** argv)
     const unsigned B = argc > 1 ? std::atoi(argv[1]) : 64, w = argc > 2 ? std::atoi(argv[2]) : 512, h = argc > 3 ? std::atoi(argv[3]) : 512;
     const unsigned ch = argc > 4 ? std::atoi(argv[4]) : 4;
     int            G  = qoipp::b200::device_count();
-    if (argc > 5) G = std::min(G, std::atoi(argv[5]));
+    if (argc > 5 && std::atoi(argv[5]) > 0) G = std::min(G, std::atoi(argv[5]));
+    const int T = argc > 6 ? std::max(1, std::atoi(argv[6])) : 1;
     if (G <= 0) {
         std::fprintf(stderr, "no CUDA device\n");
         return 2;
@@ -40,19 +43,26 @@ int main(int argc, char** argv)
     std::vector<int>         failures(G, 0), served(G, 0);
     std::vector<std::thread> threads;
     const auto               t0 = std::chrono::steady_clock::now();
-    for (int g = 0; g < G; ++g)
-        threads.emplace_back([&, g] {
+    std::vector<int> fail_t(G * T, 0), served_t(G * T, 0);
+    for (int gt = 0; gt < G * T; ++gt)
+        threads.emplace_back([&, gt] {
+            const int g = gt / T, sub = gt % T;
+            auto&     failures = fail_t;  // per thread slots: no sharing between threads
+            auto&     served   = served_t;
             qoipp::b200::set_device(g);
+            unsigned mine = 0;
             for (unsigned k = 0; k < B; ++k) {
                 if ((int)((uint64_t)k * G / B) != g) continue;  // not this GPU's image
+                if ((int)(mine++ % (unsigned)T) != sub) continue;  // not this thread's share of the GPU's images
                 auto enc = qoipp::encode(images[k], desc);
-                if (not enc) { ++failures[g]; continue; }
+                if (not enc) { ++failures[gt]; continue; }
                 auto dec = qoipp::decode(*enc);
-                if (not dec or dec->data != images[k] or qoipp::b200::device() != g) ++failures[g];
-                ++served[g];
+                if (not dec or dec->data != images[k] or qoipp::b200::device() != g) ++failures[gt];
+                ++served[gt];
             }
         });
     for (auto& t : threads) t.join();
+    for (int gt = 0; gt < G * T; ++gt) failures[gt / T] += fail_t[gt], served[gt / T] += served_t[gt];
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     int          bad = 0, total = 0;
     for (int g = 0; g < G; ++g) {

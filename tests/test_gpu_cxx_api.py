@@ -57,3 +57,14 @@ def test_thread_per_gpu_example_serves_every_gpu(tmp_path):
     print(r.stdout, r.stderr[-2000:])
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failures" in r.stdout.splitlines()[-1]
+
+
+@pytest.mark.gpu
+def test_several_host_threads_drive_one_gpu(tmp_path):
+    """The free functions are re-entrant (SURVEY 8(b) threading): six host threads encode and decode at the same time on GPU 0,
+    each through its own context and stream; every result is checked."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "qoipp_b200", "csrc", "cxx")], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(ROOT, "examples", "batch_multi_gpu"), "96", "640", "360", "4", "1", "6"], capture_output=True, text=True, timeout=600)
+    print(r.stdout, r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "96 images on 1 GPUs" in r.stdout and "0 failures" in r.stdout.splitlines()[-1]
